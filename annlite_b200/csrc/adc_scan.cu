@@ -1,0 +1,287 @@
+// adc_scan.cu -- K2: exhaustive ADC scan, plain (dist_pqcodes_to_codebooks) and fused with top-k
+// (PQIndex.search), plus the (dist, id) k-way merge used for chunk partials and shard results.
+//
+// d[n] = sum_m T[m, code[n,m]], m sequential from 0.f     bindings/pq_bindings.pyx:30-47, :52-80
+// top-k: k smallest ascending, ties by row index          pq_index.py:29-56 + annlite/math.py:94-120
+//        (numpy leaves tie order unspecified; (dist, index) is the rule the oracle fixes too)
+//
+// Mapping (scan_topk): a CTA stages QT query tables in shared memory (one per warp) and streams a
+// chunk of the code matrix; each lane scores one code row per step (coalesced code loads, L1
+// shared by the CTA's warps), and the warp keeps its query's running top-k in a register-
+// resident sorted list with a threshold test, so inserts are rare after warm-up.  Partials
+// (B, chunks, k) are merged by merge_topk_kernel.  Bound: shared-memory gather rate for N*M
+// small (C1: 80 KB of codes, L2/L1 resident), HBM reads of N*M bytes per query tile otherwise.
+#include <math_constants.h>
+
+#include "annb_internal.h"
+#include "warp_list.cuh"
+
+namespace {
+
+template <typename code_t>
+__device__ __forceinline__ float adc_lookup_row(const float *__restrict__ T, const code_t *__restrict__ row, int M,
+                                                int Ks) {
+  float r = 0.f;
+  for (int m = 0; m < M; m++) r = __fadd_rn(r, T[m * Ks + (int)row[m]]);
+  return r;
+}
+
+// specialisation for 8 one-byte codes (M = 8): one 64-bit load per row
+__device__ __forceinline__ float adc_lookup_u8x8(const float *__restrict__ T, uint2 c, int Ks) {
+  float r = 0.f;
+  r = __fadd_rn(r, T[0 * Ks + (c.x & 0xff)]);
+  r = __fadd_rn(r, T[1 * Ks + ((c.x >> 8) & 0xff)]);
+  r = __fadd_rn(r, T[2 * Ks + ((c.x >> 16) & 0xff)]);
+  r = __fadd_rn(r, T[3 * Ks + (c.x >> 24)]);
+  r = __fadd_rn(r, T[4 * Ks + (c.y & 0xff)]);
+  r = __fadd_rn(r, T[5 * Ks + ((c.y >> 8) & 0xff)]);
+  r = __fadd_rn(r, T[6 * Ks + ((c.y >> 16) & 0xff)]);
+  r = __fadd_rn(r, T[7 * Ks + (c.y >> 24)]);
+  return r;
+}
+
+template <typename code_t>
+__global__ void scan_kernel(const float *__restrict__ table, const code_t *__restrict__ codes, float *__restrict__ out,
+                            int64_t N, int M, int Ks, int table_in_smem) {
+  extern __shared__ float sT[];
+  const float *T = table;
+  if (table_in_smem) {
+    for (int i = threadIdx.x; i < M * Ks; i += blockDim.x) sT[i] = table[i];
+    __syncthreads();
+    T = sT;
+  }
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float d;
+    if (sizeof(code_t) == 1 && M == 8) {
+      uint2 c = *reinterpret_cast<const uint2 *>(codes + n * 8);
+      d = adc_lookup_u8x8(T, c, Ks);
+    } else {
+      d = adc_lookup_row<code_t>(T, codes + n * M, M, Ks);
+    }
+    out[n] = d;
+  }
+}
+
+// partial top-k of one (query, chunk): results to part_d/part_i [(b*chunks + chunk)*k ...]
+template <int EPL, typename code_t>
+__global__ void __launch_bounds__(256)
+scan_topk_kernel(const float *__restrict__ tables, const code_t *__restrict__ codes, int64_t B, int64_t N, int M, int Ks,
+                 int k, int chunks, int64_t rows_per_chunk, int table_in_smem, float *__restrict__ part_d,
+                 uint32_t *__restrict__ part_i) {
+  extern __shared__ float sT[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int W = blockDim.x >> 5;
+  const int64_t b = (int64_t)blockIdx.y * W + warp;
+  const int chunk = blockIdx.x;
+  const int TS = M * Ks;
+  const float *T = nullptr;
+  if (b < B) {
+    T = tables + b * TS;
+    if (table_in_smem) {
+      float *dst = sT + warp * TS;
+      for (int i = lane; i < TS; i += 32) dst[i] = T[i];
+      T = dst;
+    }
+  }
+  __syncwarp();
+  if (b >= B) return;
+  WarpList<EPL> L;
+  L.clear();
+  float worst = CUDART_INF_F;
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = min(N, r0 + rows_per_chunk);
+  for (int64_t base = r0; base < r1; base += 32) {
+    const int64_t n = base + lane;
+    float d = CUDART_INF_F;
+    if (n < r1) {
+      if (sizeof(code_t) == 1 && M == 8) {
+        uint2 c = *reinterpret_cast<const uint2 *>(codes + n * 8);
+        d = adc_lookup_u8x8(T, c, Ks);
+      } else {
+        d = adc_lookup_row<code_t>(T, codes + n * M, M, Ks);
+      }
+    }
+    unsigned mask = __ballot_sync(FULL_MASK, d < worst);
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float dj = __shfl_sync(FULL_MASK, d, j);
+      if (dj < worst) {
+        L.insert(dj, (uint32_t)(base + j - r0), k);
+        worst = L.key_at(k - 1);
+      }
+    }
+  }
+  // write the k best (positions 0..k-1), row index made global
+#pragma unroll
+  for (int e = 0; e < EPL; e++) {
+    const int pos = e * 32 + lane;
+    if (pos < k) {
+      const int64_t o = (b * chunks + chunk) * k + pos;
+      part_d[o] = L.k[e];
+      part_i[o] = L.v[e] == LIST_EMPTY_VAL ? LIST_EMPTY_VAL : (uint32_t)(L.v[e] + r0);
+    }
+  }
+}
+
+// Merge G sorted (ascending) lists of k (dist, id) per query into the global k best, ordered
+// by (dist, id).  One warp per query; lists are tiny (G*k entries).  Used for chunk partials
+// (ids = u32 row index -> i64) and for shard results (ids = u64 labels).
+// CellContainer.ivf_search merge: annlite/container.py:130-138 (hstack -> argsort[:limit]).
+template <typename in_id_t, typename out_id_t, int EPL>
+__global__ void merge_topk_kernel(const float *__restrict__ d_in, const in_id_t *__restrict__ i_in, int G, int64_t B, int k,
+                                  int64_t g_stride, int64_t b_stride, float *__restrict__ d_out,
+                                  out_id_t *__restrict__ i_out, in_id_t empty_in, out_id_t empty_out) {
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  // Rank-based merge: entry x gets rank = #{y : (d_y, id_y) < (d_x, id_x)}; ranks < k are written.
+  // G*k is small (<= a few thousand), O((G*k)^2 / 32) per query is negligible next to the scan / walk.
+  const int total = G * k;
+  for (int x = lane; x < total; x += 32) {
+    const int gx = x / k, px = x - gx * k;
+    const float dx = d_in[gx * g_stride + b * b_stride + px];
+    const in_id_t ix = i_in[gx * g_stride + b * b_stride + px];
+    if (ix == empty_in) continue;
+    int rank = 0;
+    for (int y = 0; y < total; y++) {
+      const int gy = y / k, py = y - gy * k;
+      const float dy = d_in[gy * g_stride + b * b_stride + py];
+      const in_id_t iy = i_in[gy * g_stride + b * b_stride + py];
+      if (iy == empty_in) continue;
+      rank += (dy < dx) || (dy == dx && (iy < ix || (iy == ix && y < x)));
+    }
+    if (rank < k) {
+      d_out[b * k + rank] = dx;
+      i_out[b * k + rank] = (out_id_t)ix;
+    }
+  }
+  // fill the tail when fewer than k valid entries exist
+  int valid = 0;
+  for (int x = lane; x < total; x += 32) {
+    const int gx = x / k, px = x - gx * k;
+    valid += i_in[gx * g_stride + b * b_stride + px] != empty_in;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(FULL_MASK, valid, o);
+  for (int p = valid + lane; p < k; p += 32) {
+    d_out[b * k + p] = CUDART_INF_F;
+    i_out[b * k + p] = empty_out;
+  }
+}
+
+}  // namespace
+
+static size_t smem_optin_limit(int device) {
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  return (size_t)v;
+}
+
+int launch_scan(annb_index *h, const float *d_table, float *d_out) {
+  const int64_t N = h->n_codes;
+  if (N == 0) return ANNB_OK;
+  const size_t tbytes = (size_t)h->M * h->Ks * sizeof(float);
+  const int in_smem = tbytes <= 96 * 1024;
+  int blocks = (int)std::min<int64_t>((N + 255) / 256, (int64_t)h->sm_count * 8);
+  if (h->code_bytes == 1) {
+    if (in_smem && tbytes > 48 * 1024)
+      ANNB_CUDA(cudaFuncSetAttribute(scan_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes));
+    scan_kernel<uint8_t><<<blocks, 256, in_smem ? tbytes : 0, h->stream>>>(d_table, (const uint8_t *)h->d_codes, d_out, N,
+                                                                         h->M, h->Ks, in_smem);
+  } else {
+    if (in_smem && tbytes > 48 * 1024)
+      ANNB_CUDA(cudaFuncSetAttribute(scan_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes));
+    scan_kernel<uint16_t><<<blocks, 256, in_smem ? tbytes : 0, h->stream>>>(d_table, (const uint16_t *)h->d_codes, d_out,
+                                                                          N, h->M, h->Ks, in_smem);
+  }
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
+template <int EPL, typename code_t>
+static int run_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int chunks, int64_t rows_per_chunk,
+                         int W, int in_smem, size_t smem, float *part_d, uint32_t *part_i) {
+  auto kern = scan_topk_kernel<EPL, code_t>;
+  if (smem > 48 * 1024) ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t done = 0;
+  while (done < B) {
+    int64_t nb = std::min<int64_t>(B - done, (int64_t)65535 * W);
+    dim3 grid((unsigned)chunks, (unsigned)((nb + W - 1) / W));
+    kern<<<grid, W * 32, smem, h->stream>>>(d_tables + done * h->M * h->Ks, (const code_t *)h->d_codes, nb, h->n_codes,
+                                            h->M, h->Ks, k, chunks, rows_per_chunk, in_smem,
+                                            part_d + done * chunks * k, part_i + done * chunks * k);
+    h->launches++;
+    ANNB_CUDA(cudaGetLastError());
+    done += nb;
+  }
+  return ANNB_OK;
+}
+
+int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists) {
+  if (B == 0) return ANNB_OK;
+  const int64_t N = h->n_codes;
+  if (k > ANNB_MAX_EF) ANNB_FAIL(ANNB_ELIMIT, "k=%d exceeds the limit %d of the register-resident top-k list", k, ANNB_MAX_EF);
+  if (N >= (int64_t)0xffffffffll) ANNB_FAIL(ANNB_ELIMIT, "scan supports < 2^32-1 rows per index (shard larger sets)");
+  const size_t tbytes = (size_t)h->M * h->Ks * sizeof(float);
+  const size_t lim = smem_optin_limit(h->device);
+  int W = 8;
+  int in_smem = 1;
+  while (W > 1 && W * tbytes > lim - 1024) W >>= 1;
+  if (W * tbytes > lim - 1024) in_smem = 0, W = 8;
+  const size_t smem = in_smem ? W * tbytes : 0;
+  // enough (tile, chunk) CTAs to fill the GPU for ~2 waves; chunks of >= 1024 rows
+  const int64_t tiles = (B + W - 1) / W;
+  int64_t want = std::max<int64_t>(1, (2LL * h->sm_count * 2 + tiles - 1) / tiles);
+  int64_t maxchunks = std::max<int64_t>(1, N / 1024);
+  int chunks = (int)std::min<int64_t>(std::min<int64_t>(want, maxchunks), 128);
+  int64_t rows_per_chunk = (N + chunks - 1) / chunks;
+  rows_per_chunk = (rows_per_chunk + 31) / 32 * 32;
+  chunks = (int)std::max<int64_t>(1, (N + rows_per_chunk - 1) / rows_per_chunk);
+
+  float *part_d;
+  uint32_t *part_i;
+  int rc;
+  if ((rc = annb_scratch(h, 16, (size_t)B * chunks * k * sizeof(float), (void **)&part_d))) return rc;
+  if ((rc = annb_scratch(h, 17, (size_t)B * chunks * k * sizeof(uint32_t), (void **)&part_i))) return rc;
+
+  const int epl = (k + 31) / 32;
+#define ST_CASE(E)                                                                                                    \
+  if (h->code_bytes == 1)                                                                                             \
+    rc = run_scan_topk<E, uint8_t>(h, d_tables, B, k, chunks, rows_per_chunk, W, in_smem, smem, part_d, part_i);      \
+  else                                                                                                                \
+    rc = run_scan_topk<E, uint16_t>(h, d_tables, B, k, chunks, rows_per_chunk, W, in_smem, smem, part_d, part_i);
+  if (epl <= 1) {
+    ST_CASE(1)
+  } else if (epl <= 2) {
+    ST_CASE(2)
+  } else if (epl <= 4) {
+    ST_CASE(4)
+  } else if (epl <= 8) {
+    ST_CASE(8)
+  } else {
+    ST_CASE(16)
+  }
+#undef ST_CASE
+  if (rc) return rc;
+  // merge chunk partials: lists laid out [b][chunk][k] => g_stride = k, b_stride = chunks*k
+  const int warps = 4;
+  merge_topk_kernel<uint32_t, int64_t, 1><<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, h->stream>>>(
+      part_d, part_i, chunks, B, k, (int64_t)k, (int64_t)chunks * k, d_dists, d_ids, LIST_EMPTY_VAL, (int64_t)-1);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
+int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k,
+                      uint64_t *labels_out, float *dists_out) {
+  if (B == 0) return ANNB_OK;
+  const int warps = 4;
+  // shard results laid out [g][b][k] => g_stride = B*k, b_stride = k
+  merge_topk_kernel<uint64_t, uint64_t, 1><<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, h->stream>>>(
+      dists, labels, G, B, k, B * (int64_t)k, (int64_t)k, dists_out, labels_out, (uint64_t)UINT64_MAX, (uint64_t)UINT64_MAX);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}

@@ -1,0 +1,194 @@
+// annb_internal.h -- shared declarations of libannlite_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/annb.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void annb_set_error(const char *fmt, ...);
+#define ANNB_FAIL(code, ...)     \
+  do {                           \
+    annb_set_error(__VA_ARGS__); \
+    return (code);               \
+  } while (0)
+#define ANNB_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      annb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
+      return ANNB_ECUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Host graph: same memory layout as the reference (hnswalg.h:45-49, :66) so that save/load,
+// pickle state and builder parity are byte-for-byte checks.
+//   level-0 record: [u16 count][u8 flags(bit0 = deleted)][u8 pad][maxM0 x u32 links]
+//                   [M x code][u64 label]
+//   upper record  : per level [u16 count][u16 pad][maxM x u32 links]
+// ------------------------------------------------------------------------------------------
+struct HostGraph {
+  // geometry
+  int M = 16, maxM = 16, maxM0 = 32, ef_construction = 200;
+  double mult = 0.0;
+  uint64_t seed = 100;
+  size_t code_row_bytes = 0;  // n_subvectors * code_bytes
+  size_t size_links_level0 = 0, size_per_elem = 0, offset_data = 0, label_offset = 0;
+  size_t size_links_per_elem = 0;
+  // state
+  int64_t max_elements = 0;
+  std::atomic<int64_t> count{0};
+  int32_t maxlevel = -1;
+  uint32_t enterpoint = 0xFFFFFFFFu;
+  int64_t num_deleted = 0;
+  uint8_t *level0 = nullptr;             // max_elements * size_per_elem
+  std::vector<uint8_t *> upper;          // per element: levels * size_links_per_elem (or null)
+  std::vector<int32_t> levels;           // element_levels_
+  std::unordered_map<uint64_t, uint32_t> label_lookup;
+  bool inited = false;
+  std::default_random_engine level_gen;  // hnswalg.h:130
+
+  ~HostGraph();
+  void clear();
+  int init(int64_t max_elems, int M_, int efc, uint64_t seed_, size_t code_row_bytes_);
+  int resize(int64_t new_max);
+  uint8_t *rec0(uint32_t id) const { return level0 + (size_t)id * size_per_elem; }
+  uint8_t *list_at(uint32_t id, int level) const {
+    return level == 0 ? rec0(id) : upper[id] + (size_t)(level - 1) * size_links_per_elem;
+  }
+  const uint8_t *code(uint32_t id) const { return rec0(id) + offset_data; }
+  uint64_t label(uint32_t id) const;
+  bool deleted(uint32_t id) const { return rec0(id)[2] & 1; }
+  int load_file(const char *path, int64_t max_elements_i, size_t code_row_bytes_);
+  int save_file(const char *path) const;
+};
+
+// per-thread scratch + algorithm of the host builder (hnsw_build.cpp)
+struct BuildContext;
+
+// ------------------------------------------------------------------------------------------
+// Device graph ("walk layout"): each node's adjacency is co-located with the PQ codes of its
+// neighbours so one hop of the walk is ONE contiguous read.
+//   level-0 record r0[id]  : [maxM0 x u32 link (0xFFFFFFFF = empty)][pad to 16][maxM0 x code_row]
+//                            [pad to 16]                                                  (rec0_bytes)
+//   upper record  up[l][r] : [maxM x u32 link = record index at level l][pad to 16][maxM x code_row]
+//                            [pad to 8][u32 node id][u32 down = record index at level l-1
+//                            (node id if l==1)][pad to 16]                                (recu_bytes)
+// ------------------------------------------------------------------------------------------
+#define ANNB_MAX_LEVELS 32
+struct GraphDev {
+  const uint8_t *rec0;     // n * rec0_bytes
+  const uint8_t *up;       // all upper levels, level l starts at up_off[l] (bytes)
+  const uint64_t *labels;  // n
+  const uint32_t *deleted; // bitmap by internal id (n/32 words) or nullptr when none deleted
+  uint64_t up_off[ANNB_MAX_LEVELS];
+  int64_t n;
+  int32_t maxlevel;
+  uint32_t ep_node;  // entry node id
+  uint32_t ep_rec;   // its record index at level maxlevel (== ep_node when maxlevel == 0)
+  int32_t maxM, maxM0;
+  int32_t rec0_bytes, recu_bytes;
+  int32_t code_off0;   // byte offset of the neighbour codes inside a level-0 record (16-aligned)
+  int32_t code_offu;   // same for upper records
+  int32_t tail_offu;   // byte offset of {u32 node id, u32 down} inside an upper record (8-aligned)
+  int32_t M, Ks, code_bytes, code_row;  // code_row = M*code_bytes
+  alignas(16) uint8_t ep_code[128];     // code of the entry node (code_row <= 128 bytes)
+};
+
+struct SearchParams {
+  const float *tables;  // (B, M, Ks)
+  int64_t B;
+  int k, ef;
+  const uint32_t *filter;  // bitmap by internal id, or nullptr
+  uint64_t *out_labels;    // (B,k)
+  float *out_dists;        // (B,k)
+  int32_t *out_found;      // (B)
+  int64_t *out_stats;      // (B,3) or nullptr
+  unsigned int *work_counter;
+  // general-mode scratch (per warp slot)
+  uint32_t *visited;      // slots * visited_words
+  int64_t visited_words;
+  uint32_t *touched;      // slots * touched_cap
+  int touched_cap;
+  uint64_t *cand;         // slots * cand_cap  (packed: float bits << 32 | id)
+  int cand_cap;
+  int32_t *overflow_flag;
+};
+
+// ------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------
+struct annb_index {
+  int device = 0;
+  int metric = ANNB_METRIC_L2;
+  int dim = 0, M = 0, Ks = 0, ds = 0, code_bytes = 1;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr};  // [0,1] K1, [2,3] K3, [4,5] K2
+  std::mutex mu;
+
+  float *d_codebook = nullptr;
+  std::vector<float> h_codebook;
+
+  // flat code matrix for K2
+  uint8_t *d_codes = nullptr;
+  int64_t n_codes = 0;
+
+  // graph
+  HostGraph g;
+  bool dev_dirty = true;
+  bool deleted_dirty = false;
+  GraphDev gd{};
+  uint8_t *d_rec0 = nullptr, *d_up = nullptr;
+  uint64_t *d_labels = nullptr;
+  uint32_t *d_deleted = nullptr;
+  size_t cap_rec0 = 0, cap_up = 0, cap_labels = 0, cap_deleted = 0;
+
+  // scratch (grown on demand)
+  void *d_scratch[18] = {nullptr};
+  size_t scratch_cap[18] = {0};
+  void *h_pinned[4] = {nullptr};
+  size_t pinned_cap[4] = {0};
+
+  uint64_t max_label = 0;          // largest label in the graph (filter bitmap sizing)
+  bool labels_identity = true;     // label[i] == i for all nodes
+  float last_table_ms = 0, last_search_ms = 0, last_scan_ms = 0;
+  int64_t launches = 0;
+  // options
+  int64_t opt_warps_per_cta = 0;   // 0 = auto
+  int64_t opt_ctas_per_sm = 0;     // 0 = auto
+  int64_t opt_force_general = 0;   // use the general (visited + candidate heap) walk always
+  int64_t opt_timing = 1;
+};
+
+int annb_scratch(annb_index *h, int slot, size_t bytes, void **out);
+int annb_pinned(annb_index *h, int slot, size_t bytes, void **out);
+
+// kernels (launchers)
+int launch_l2_normalize(annb_index *h, float *x, int64_t B, int D);
+int launch_adc_table(annb_index *h, const float *d_queries, int64_t B, float *d_out);
+int launch_scan(annb_index *h, const float *d_table, float *d_out);
+int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists);
+int launch_encode(annb_index *h, const float *d_x, int64_t n, void *d_codes);
+int launch_pack_rec0(annb_index *h, const uint8_t *d_level0_raw, int64_t n);
+int launch_search(annb_index *h, const SearchParams &p, bool general);
+int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k,
+                      uint64_t *labels_out, float *dists_out);
+int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t n_filter, uint32_t *d_by_label,
+                         uint32_t *d_by_id);
+
+// host builder
+int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels, int64_t n, int num_threads,
+                     const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows);
+int sync_device_graph(annb_index *h);

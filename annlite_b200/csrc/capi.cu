@@ -1,0 +1,873 @@
+// capi.cu -- the extern "C" boundary of libannlite_b200.so (see include/annb.h).
+#include <math_constants.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "annb_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void annb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+enum {
+  S_QUERIES = 0, S_TABLES, S_OUT_D, S_OUT_L, S_COUNTER, S_VISITED, S_TOUCHED, S_CAND,
+  S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I
+};
+
+int annb_scratch(annb_index *h, int slot, size_t bytes, void **out) {
+  if (bytes == 0) bytes = 16;
+  if (h->scratch_cap[slot] < bytes) {
+    if (h->d_scratch[slot]) {
+      ANNB_CUDA(cudaStreamSynchronize(h->stream));
+      ANNB_CUDA(cudaFree(h->d_scratch[slot]));
+      h->d_scratch[slot] = nullptr;
+      h->scratch_cap[slot] = 0;
+    }
+    size_t cap = bytes + bytes / 4;
+    cap = (cap + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&h->d_scratch[slot], cap);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cap = (bytes + 255) / 256 * 256;
+      e = cudaMalloc(&h->d_scratch[slot], cap);
+    }
+    if (e != cudaSuccess) ANNB_FAIL(ANNB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", cap, cudaGetErrorString(e));
+    h->scratch_cap[slot] = cap;
+  }
+  *out = h->d_scratch[slot];
+  return ANNB_OK;
+}
+
+int annb_pinned(annb_index *h, int slot, size_t bytes, void **out) {
+  if (h->pinned_cap[slot] < bytes) {
+    if (h->h_pinned[slot]) {
+      ANNB_CUDA(cudaStreamSynchronize(h->stream));
+      ANNB_CUDA(cudaFreeHost(h->h_pinned[slot]));
+      h->h_pinned[slot] = nullptr;
+      h->pinned_cap[slot] = 0;
+    }
+    ANNB_CUDA(cudaMallocHost(&h->h_pinned[slot], bytes));
+    h->pinned_cap[slot] = bytes;
+  }
+  *out = h->h_pinned[slot];
+  return ANNB_OK;
+}
+
+// Host-only handles (device == -1) exist for the graph container alone -- file I/O, pickle state and
+// the host-side insertion algorithm fed with caller-supplied tables.  Every compute entry point
+// (tables, scan, encode, search, merge, add_items from vectors) requires a GPU: ANNB_NEED_GPU.
+#define ANNB_ENTER(h)                                                        \
+  if (!(h)) ANNB_FAIL(ANNB_EINVAL, "null index handle");                     \
+  std::lock_guard<std::mutex> _lk((h)->mu);                                  \
+  if ((h)->device >= 0) ANNB_CUDA(cudaSetDevice((h)->device))
+#define ANNB_NEED_GPU(h) \
+  if ((h)->device < 0) ANNB_FAIL(ANNB_ENODEVICE, "this handle is host-only (graph I/O); compute needs a CUDA device: annlite_b200 has no CPU fallback")
+
+#define ANNB_TRY(expr)       \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+// stage an input: returns a device pointer (the caller's own if it already is one)
+static int stage_in(annb_index *h, const void *p, int space, size_t bytes, int slot, const void **out) {
+  if (space == ANNB_DEVICE) {
+    *out = p;
+    return ANNB_OK;
+  }
+  void *d;
+  ANNB_TRY(annb_scratch(h, slot, bytes, &d));
+  ANNB_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, h->stream));
+  *out = d;
+  return ANNB_OK;
+}
+
+extern "C" {
+
+int annb_version(void) { return ANNB_VERSION; }
+const char *annb_last_error(void) { return g_err; }
+
+int annb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int annb_create(int device, int metric, int dim, int n_subvectors, int n_clusters, annb_index_t **out) {
+  if (!out) ANNB_FAIL(ANNB_EINVAL, "out is null");
+  *out = nullptr;
+  if (metric < ANNB_METRIC_L2 || metric > ANNB_METRIC_COSINE) ANNB_FAIL(ANNB_EINVAL, "Space name must be one of l2, ip, or cosine.");
+  if (dim <= 0 || n_subvectors <= 0 || n_clusters <= 0) ANNB_FAIL(ANNB_EINVAL, "dim, n_subvectors and n_clusters must be positive");
+  if (dim % n_subvectors != 0)
+    ANNB_FAIL(ANNB_EINVAL, "Initialization Error, expect HNSW.dim == PQ.n_subvector*PQ.d_subvector, but got:\nHNSW.dim =%d, n_subvectors=%d", dim, n_subvectors);
+  if (n_clusters > 65536)
+    ANNB_FAIL(ANNB_ELIMIT, "PQ clustering exceed the maximum, annlite set the maximum of clusters = 65536, but got PQ.n_clusters=%d", n_clusters);
+  if (device != -1) {
+    int ndev = annb_device_count();
+    if (ndev <= 0) ANNB_FAIL(ANNB_ENODEVICE, "no CUDA device available: annlite_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) ANNB_FAIL(ANNB_EINVAL, "device %d out of range (have %d)", device, ndev);
+    ANNB_CUDA(cudaSetDevice(device));
+  }
+  annb_index *h = new annb_index();
+  h->device = device;
+  h->metric = metric;
+  h->dim = dim;
+  h->M = n_subvectors;
+  h->Ks = n_clusters;
+  h->ds = dim / n_subvectors;
+  h->code_bytes = n_clusters <= 256 ? 1 : 2;
+  if ((size_t)h->M * h->code_bytes > 128) {
+    delete h;
+    ANNB_FAIL(ANNB_ELIMIT, "code rows wider than 128 bytes are not supported (n_subvectors=%d)", n_subvectors);
+  }
+  if (device < 0) {
+    *out = h;
+    return ANNB_OK;
+  }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
+  if (e != cudaSuccess) {
+    annb_set_error("CUDA error %s while creating stream/events", cudaGetErrorString(e));
+    delete h;
+    return ANNB_ECUDA;
+  }
+  *out = h;
+  return ANNB_OK;
+}
+
+int annb_destroy(annb_index_t *h) {
+  if (!h) return ANNB_OK;
+  if (h->device < 0) {
+    delete h;
+    return ANNB_OK;
+  }
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto &p : h->d_scratch)
+    if (p) cudaFree(p);
+  for (auto &p : h->h_pinned)
+    if (p) cudaFreeHost(p);
+  if (h->d_codebook) cudaFree(h->d_codebook);
+  if (h->d_codes) cudaFree(h->d_codes);
+  if (h->d_rec0) cudaFree(h->d_rec0);
+  if (h->d_up) cudaFree(h->d_up);
+  if (h->d_labels) cudaFree(h->d_labels);
+  if (h->d_deleted) cudaFree(h->d_deleted);
+  for (int i = 0; i < 6; i++)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return ANNB_OK;
+}
+
+int annb_set_codebook(annb_index_t *h, const float *codebook, int space) {
+  ANNB_ENTER(h);
+  if (!codebook) ANNB_FAIL(ANNB_EINVAL, "Passed PQ class is none");
+  const size_t bytes = (size_t)h->M * h->Ks * h->ds * sizeof(float);
+  ANNB_NEED_GPU(h);
+  if (!h->d_codebook) ANNB_CUDA(cudaMalloc(&h->d_codebook, bytes));
+  ANNB_CUDA(cudaMemcpyAsync(h->d_codebook, codebook, bytes, space == ANNB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                            h->stream));
+  h->h_codebook.resize((size_t)h->M * h->Ks * h->ds);
+  if (space == ANNB_DEVICE)
+    ANNB_CUDA(cudaMemcpyAsync(h->h_codebook.data(), codebook, bytes, cudaMemcpyDeviceToHost, h->stream));
+  else
+    memcpy(h->h_codebook.data(), codebook, bytes);
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  return ANNB_OK;
+}
+
+int annb_stream(annb_index_t *h, uint64_t *stream_out) {
+  if (!h || !stream_out) ANNB_FAIL(ANNB_EINVAL, "null argument");
+  *stream_out = (uint64_t)(uintptr_t)h->stream;
+  return ANNB_OK;
+}
+
+int annb_sync(annb_index_t *h) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  return ANNB_OK;
+}
+
+// ---- K1 ---------------------------------------------------------------------------------------
+// queries (host/device) -> device tables; `d_tables_out` receives the device pointer used.
+static int build_tables(annb_index *h, const float *queries, int q_space, int64_t B, int normalize, float *d_tables) {
+  if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
+  const size_t qbytes = (size_t)B * h->dim * sizeof(float);
+  const float *dq;
+  if (normalize > 0 && q_space == ANNB_DEVICE) {  // never modify the caller's buffer
+    void *d;
+    ANNB_TRY(annb_scratch(h, S_QUERIES, qbytes, &d));
+    ANNB_CUDA(cudaMemcpyAsync(d, queries, qbytes, cudaMemcpyDeviceToDevice, h->stream));
+    dq = (const float *)d;
+  } else {
+    ANNB_TRY(stage_in(h, queries, q_space, qbytes, S_QUERIES, (const void **)&dq));
+  }
+  if (h->opt_timing) cudaEventRecord(h->ev[0], h->stream);
+  for (int r = 0; r < normalize; r++) ANNB_TRY(launch_l2_normalize(h, const_cast<float *>(dq), B, h->dim));
+  ANNB_TRY(launch_adc_table(h, dq, B, d_tables));
+  if (h->opt_timing) cudaEventRecord(h->ev[1], h->stream);
+  return ANNB_OK;
+}
+
+int annb_adc_table(annb_index_t *h, const float *queries, int q_space, int64_t B, int normalize, float *out, int out_space) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (B < 0 || (B > 0 && (!queries || !out))) ANNB_FAIL(ANNB_EINVAL, "null queries/out");
+  if (B == 0) return ANNB_OK;
+  const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
+  float *d_tables = out;
+  if (out_space != ANNB_DEVICE) ANNB_TRY(annb_scratch(h, S_TABLES, tbytes, (void **)&d_tables));
+  ANNB_TRY(build_tables(h, queries, q_space, B, normalize, d_tables));
+  if (out_space != ANNB_DEVICE) {
+    ANNB_CUDA(cudaMemcpyAsync(out, d_tables, tbytes, cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return ANNB_OK;
+}
+
+// ---- K2 ---------------------------------------------------------------------------------------
+int annb_set_codes(annb_index_t *h, const void *codes, int space, int64_t n) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (n < 0 || (n > 0 && !codes)) ANNB_FAIL(ANNB_EINVAL, "null codes");
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->d_codes) {
+    ANNB_CUDA(cudaFree(h->d_codes));
+    h->d_codes = nullptr;
+  }
+  h->n_codes = 0;
+  if (n == 0) return ANNB_OK;
+  const size_t bytes = (size_t)n * h->M * h->code_bytes;
+  ANNB_CUDA(cudaMalloc(&h->d_codes, bytes + 16));
+  ANNB_CUDA(cudaMemcpyAsync(h->d_codes, codes, bytes, space == ANNB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                            h->stream));
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  h->n_codes = n;
+  return ANNB_OK;
+}
+
+int annb_scan(annb_index_t *h, const float *table, int t_space, float *out_dists, int out_space) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (!table || !out_dists) ANNB_FAIL(ANNB_EINVAL, "null table/out");
+  if (!h->d_codes) ANNB_FAIL(ANNB_ESTATE, "no code matrix: call annb_set_codes first");
+  const float *dt;
+  ANNB_TRY(stage_in(h, table, t_space, (size_t)h->M * h->Ks * sizeof(float), S_TABLES, (const void **)&dt));
+  float *dout = out_dists;
+  if (out_space != ANNB_DEVICE) ANNB_TRY(annb_scratch(h, S_OUT_D, (size_t)h->n_codes * sizeof(float), (void **)&dout));
+  if (h->opt_timing) cudaEventRecord(h->ev[4], h->stream);
+  ANNB_TRY(launch_scan(h, dt, dout));
+  if (h->opt_timing) cudaEventRecord(h->ev[5], h->stream);
+  if (out_space != ANNB_DEVICE) {
+    ANNB_CUDA(cudaMemcpyAsync(out_dists, dout, (size_t)h->n_codes * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return ANNB_OK;
+}
+
+int annb_scan_topk(annb_index_t *h, const float *queries, const float *tables, int in_space, int64_t B, int k, int64_t *ids,
+                   float *dists, int out_space) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if ((queries == nullptr) == (tables == nullptr)) ANNB_FAIL(ANNB_EINVAL, "exactly one of queries / tables must be given");
+  if (B < 0 || k <= 0 || !ids || !dists) ANNB_FAIL(ANNB_EINVAL, "bad B/k/outputs");
+  if (!h->d_codes) ANNB_FAIL(ANNB_ESTATE, "no code matrix: call annb_set_codes first");
+  if (B == 0) return ANNB_OK;
+  const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
+  const float *dt;
+  if (tables) {
+    ANNB_TRY(stage_in(h, tables, in_space, tbytes, S_TABLES, (const void **)&dt));
+  } else {
+    float *t;
+    ANNB_TRY(annb_scratch(h, S_TABLES, tbytes, (void **)&t));
+    // PQIndex.search builds its table with precompute_adc (L2 form, no normalisation): pq.py:200-224
+    ANNB_TRY(build_tables(h, queries, in_space, B, 0, t));
+    dt = t;
+  }
+  int64_t *dids = ids;
+  float *dd = dists;
+  if (out_space != ANNB_DEVICE) {
+    ANNB_TRY(annb_scratch(h, S_OUT_L, (size_t)B * k * sizeof(int64_t), (void **)&dids));
+    ANNB_TRY(annb_scratch(h, S_OUT_D, (size_t)B * k * sizeof(float), (void **)&dd));
+  }
+  if (h->opt_timing) cudaEventRecord(h->ev[4], h->stream);
+  ANNB_TRY(launch_scan_topk(h, dt, B, k, dids, dd));
+  if (h->opt_timing) cudaEventRecord(h->ev[5], h->stream);
+  if (out_space != ANNB_DEVICE) {
+    ANNB_CUDA(cudaMemcpyAsync(ids, dids, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaMemcpyAsync(dists, dd, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return ANNB_OK;
+}
+
+// ---- graph ------------------------------------------------------------------------------------
+int annb_init_graph(annb_index_t *h, int64_t max_elements, int M, int ef_construction, uint64_t random_seed) {
+  ANNB_ENTER(h);
+  if (max_elements < 0 || M <= 0 || M > 1024) ANNB_FAIL(ANNB_EINVAL, "bad max_elements / M");
+  ANNB_TRY(h->g.init(max_elements, M, ef_construction, random_seed, (size_t)h->M * h->code_bytes));
+  h->dev_dirty = true;
+  return ANNB_OK;
+}
+
+int annb_load_index(annb_index_t *h, const char *path, int64_t max_elements) {
+  ANNB_ENTER(h);
+  if (!path) ANNB_FAIL(ANNB_EINVAL, "null path");
+  ANNB_TRY(h->g.load_file(path, max_elements, (size_t)h->M * h->code_bytes));
+  h->dev_dirty = true;
+  return ANNB_OK;
+}
+
+int annb_save_index(annb_index_t *h, const char *path) {
+  ANNB_ENTER(h);
+  if (!path) ANNB_FAIL(ANNB_EINVAL, "null path");
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  return h->g.save_file(path);
+}
+
+int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_data_per_element, uint64_t offset_data,
+                   uint64_t label_offset, const uint8_t *link_lists, const int32_t *element_levels,
+                   uint64_t size_links_per_element, int64_t cur_element_count, int64_t max_elements, int32_t max_level,
+                   uint32_t enterpoint_node, int max_M, int max_M0, int M, int ef_construction, double mult) {
+  ANNB_ENTER(h);
+  HostGraph &g = h->g;
+  const size_t crow = (size_t)h->M * h->code_bytes;
+  if (max_elements < cur_element_count) max_elements = cur_element_count;
+  ANNB_TRY(g.init(max_elements, M, ef_construction, 100, crow));
+  if (g.size_per_elem != size_data_per_element) ANNB_FAIL(ANNB_EINVAL, "Invalid value of size_data_per_element_ ");
+  if (g.label_offset != label_offset) ANNB_FAIL(ANNB_EINVAL, "Invalid value of label_offset_ ");
+  if (g.offset_data != offset_data) ANNB_FAIL(ANNB_EINVAL, "Invalid value of offsetData_ ");
+  if (g.maxM != max_M) ANNB_FAIL(ANNB_EINVAL, "Invalid value of maxM_ ");
+  if (g.maxM0 != max_M0) ANNB_FAIL(ANNB_EINVAL, "Invalid value of maxM0_ ");
+  if (g.size_links_per_elem != size_links_per_element) ANNB_FAIL(ANNB_EINVAL, "Invalid value of size_links_per_element_ ");
+  g.mult = mult;
+  g.maxlevel = max_level;
+  g.enterpoint = enterpoint_node;
+  const size_t n = (size_t)cur_element_count;
+  if (n) memcpy(g.level0, data_level0, n * g.size_per_elem);
+  size_t off = 0;
+  for (size_t i = 0; i < n; i++) {
+    g.levels[i] = element_levels[i];
+    if (element_levels[i] > 0) {
+      const size_t sz = g.size_links_per_elem * (size_t)element_levels[i];
+      g.upper[i] = (uint8_t *)malloc(sz);
+      if (!g.upper[i]) ANNB_FAIL(ANNB_ENOMEM, "Not enough memory: loadIndex failed to allocate linklist");
+      memcpy(g.upper[i], link_lists + off, sz);
+      off += sz;
+    }
+  }
+  g.count = (int64_t)n;
+  g.num_deleted = 0;
+  g.label_lookup.reserve(n);
+  for (size_t i = 0; i < n; i++) {
+    g.label_lookup[g.label((uint32_t)i)] = (uint32_t)i;
+    if (g.deleted((uint32_t)i)) g.num_deleted++;
+  }
+  h->dev_dirty = true;
+  return ANNB_OK;
+}
+
+int annb_graph_info(annb_index_t *h, int64_t *cur_element_count, int64_t *max_elements, uint64_t *size_data_per_element,
+                    uint64_t *link_lists_bytes, int32_t *max_level, uint32_t *enterpoint_node, int *max_M, int *max_M0, int *M,
+                    int *ef_construction, double *mult) {
+  ANNB_ENTER(h);
+  HostGraph &g = h->g;
+  if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  const int64_t n = g.count.load();
+  uint64_t lb = 0;
+  for (int64_t i = 0; i < n; i++)
+    if (g.levels[i] > 0) lb += g.size_links_per_elem * (uint64_t)g.levels[i];
+  if (cur_element_count) *cur_element_count = n;
+  if (max_elements) *max_elements = g.max_elements;
+  if (size_data_per_element) *size_data_per_element = g.size_per_elem;
+  if (link_lists_bytes) *link_lists_bytes = lb;
+  if (max_level) *max_level = g.maxlevel;
+  if (enterpoint_node) *enterpoint_node = g.enterpoint;
+  if (max_M) *max_M = g.maxM;
+  if (max_M0) *max_M0 = g.maxM0;
+  if (M) *M = g.M;
+  if (ef_construction) *ef_construction = g.ef_construction;
+  if (mult) *mult = g.mult;
+  return ANNB_OK;
+}
+
+int annb_get_graph(annb_index_t *h, uint8_t *data_level0, uint8_t *link_lists, int32_t *element_levels) {
+  ANNB_ENTER(h);
+  HostGraph &g = h->g;
+  if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  const size_t n = (size_t)g.count.load();
+  if (data_level0 && n) memcpy(data_level0, g.level0, n * g.size_per_elem);
+  size_t off = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (element_levels) element_levels[i] = g.levels[i];
+    if (g.levels[i] > 0) {
+      const size_t sz = g.size_links_per_elem * (size_t)g.levels[i];
+      if (link_lists) memcpy(link_lists + off, g.upper[i], sz);
+      off += sz;
+    }
+  }
+  return ANNB_OK;
+}
+
+int annb_encode(annb_index_t *h, const float *vectors, int v_space, int64_t n, void *codes, int c_space) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (n < 0 || (n > 0 && (!vectors || !codes))) ANNB_FAIL(ANNB_EINVAL, "null vectors/codes");
+  if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
+  if (n == 0) return ANNB_OK;
+  const float *dx;
+  ANNB_TRY(stage_in(h, vectors, v_space, (size_t)n * h->dim * sizeof(float), S_QUERIES, (const void **)&dx));
+  void *dc = codes;
+  const size_t cbytes = (size_t)n * h->M * h->code_bytes;
+  if (c_space != ANNB_DEVICE) ANNB_TRY(annb_scratch(h, S_CODES, cbytes, &dc));
+  ANNB_TRY(launch_encode(h, dx, n, dc));
+  if (c_space != ANNB_DEVICE) {
+    ANNB_CUDA(cudaMemcpyAsync(codes, dc, cbytes, cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return ANNB_OK;
+}
+
+// add_items: tables for each chunk of rows come from K1, double-buffered through pinned memory
+struct TableFeed {
+  annb_index *h;
+  const float *vectors;  // host
+  int64_t n, chunk_rows;
+  float *pinned[2];
+  cudaEvent_t done[2];
+  int64_t have_first[2];
+  int rc;
+};
+static int feed_launch(TableFeed *f, int buf, int64_t first) {
+  annb_index *h = f->h;
+  const int64_t cnt = std::min(f->chunk_rows, f->n - first);
+  float *dq, *dt;
+  int rc;
+  const int qslot = buf ? S_MISC : S_QUERIES, tslot = buf ? S_OUT_D : S_TABLES;
+  if ((rc = annb_scratch(h, qslot, (size_t)f->chunk_rows * h->dim * sizeof(float), (void **)&dq))) return rc;
+  if ((rc = annb_scratch(h, tslot, (size_t)f->chunk_rows * h->M * h->Ks * sizeof(float), (void **)&dt))) return rc;
+  ANNB_CUDA(cudaMemcpyAsync(dq, f->vectors + (size_t)first * h->dim, (size_t)cnt * h->dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // get_dist_mat re-normalises for COSINE (pq.py:309-310) on top of pre_process's pass
+  if (h->metric == ANNB_METRIC_COSINE && (rc = launch_l2_normalize(h, dq, cnt, h->dim))) return rc;
+  if ((rc = launch_adc_table(h, dq, cnt, dt))) return rc;
+  ANNB_CUDA(cudaMemcpyAsync(f->pinned[buf], dt, (size_t)cnt * h->M * h->Ks * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  ANNB_CUDA(cudaEventRecord(f->done[buf], h->stream));
+  f->have_first[buf] = first;
+  return ANNB_OK;
+}
+static const float *feed_next(void *ctx, int64_t first, int64_t cnt) {
+  TableFeed *f = (TableFeed *)ctx;
+  (void)cnt;
+  const int buf = (int)((first / f->chunk_rows) & 1);
+  if (f->have_first[buf] != first && (f->rc = feed_launch(f, buf, first))) return nullptr;
+  if (cudaEventSynchronize(f->done[buf]) != cudaSuccess) {
+    annb_set_error("CUDA error while building insertion tables");
+    f->rc = ANNB_ECUDA;
+    return nullptr;
+  }
+  const int64_t nxt = first + f->chunk_rows;
+  if (nxt < f->n && (f->rc = feed_launch(f, buf ^ 1, nxt))) return nullptr;
+  return f->pinned[buf];
+}
+
+int annb_add_items(annb_index_t *h, const float *vectors, const void *codes, const uint64_t *labels, int64_t n, int num_threads) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (n < 0 || (n > 0 && (!vectors || !labels))) ANNB_FAIL(ANNB_EINVAL, "null vectors/labels");
+  if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph first");
+  if (n == 0) return ANNB_OK;
+  const size_t crow = (size_t)h->M * h->code_bytes;
+  std::vector<uint8_t> own_codes;
+  const uint8_t *hc = (const uint8_t *)codes;
+  if (!hc) {  // PQCodec.encode on the GPU, chunked
+    own_codes.resize((size_t)n * crow);
+    const int64_t step = 1 << 18;
+    for (int64_t s = 0; s < n; s += step) {
+      const int64_t c = std::min(step, n - s);
+      float *dx;
+      void *dc;
+      ANNB_TRY(annb_scratch(h, S_QUERIES, (size_t)c * h->dim * sizeof(float), (void **)&dx));
+      ANNB_TRY(annb_scratch(h, S_CODES, (size_t)c * crow, &dc));
+      ANNB_CUDA(cudaMemcpyAsync(dx, vectors + (size_t)s * h->dim, (size_t)c * h->dim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      ANNB_TRY(launch_encode(h, dx, c, dc));
+      ANNB_CUDA(cudaMemcpyAsync(own_codes.data() + (size_t)s * crow, dc, (size_t)c * crow, cudaMemcpyDeviceToHost, h->stream));
+      ANNB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    hc = own_codes.data();
+  }
+  TableFeed f;
+  f.h = h;
+  f.vectors = vectors;
+  f.n = n;
+  const size_t TS = (size_t)h->M * h->Ks;
+  f.chunk_rows = std::max<int64_t>(64, std::min<int64_t>(8192, (int64_t)((64u << 20) / (TS * sizeof(float)))));
+  f.rc = 0;
+  for (int b = 0; b < 2; b++) {
+    ANNB_TRY(annb_pinned(h, b, (size_t)f.chunk_rows * TS * sizeof(float), (void **)&f.pinned[b]));
+    ANNB_CUDA(cudaEventCreateWithFlags(&f.done[b], cudaEventDisableTiming));
+    f.have_first[b] = -1;
+  }
+  int rc = hnsw_insert_rows(h, hc, labels, n, num_threads, feed_next, &f, f.chunk_rows);
+  cudaStreamSynchronize(h->stream);
+  for (int b = 0; b < 2; b++) cudaEventDestroy(f.done[b]);
+  h->dev_dirty = true;
+  if (rc == ANNB_ECUDA && f.rc) return f.rc;
+  return rc;
+}
+
+struct HostTables {
+  const float *tables;
+  size_t TS;
+};
+static const float *host_tables_next(void *ctx, int64_t first, int64_t) {
+  HostTables *t = (HostTables *)ctx;
+  return t->tables + (size_t)first * t->TS;
+}
+int annb_add_items_with_tables(annb_index_t *h, const void *codes, const float *tables, const uint64_t *labels, int64_t n,
+                               int num_threads) {
+  ANNB_ENTER(h);
+  if (n < 0 || (n > 0 && (!codes || !tables || !labels))) ANNB_FAIL(ANNB_EINVAL, "null codes/tables/labels");
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph first");
+  if (n == 0) return ANNB_OK;
+  HostTables t{tables, (size_t)h->M * h->Ks};
+  int rc = hnsw_insert_rows(h, (const uint8_t *)codes, labels, n, num_threads, host_tables_next, &t, n);
+  h->dev_dirty = true;
+  return rc;
+}
+
+int annb_resize_index(annb_index_t *h, int64_t new_max_elements) {
+  ANNB_ENTER(h);
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  return h->g.resize(new_max_elements);
+}
+
+static int set_deleted(annb_index *h, uint64_t label, bool del) {
+  HostGraph &g = h->g;
+  auto it = g.label_lookup.find(label);
+  if (it == g.label_lookup.end()) ANNB_FAIL(ANNB_ENOTFOUND, "Label not found");
+  uint8_t *flags = g.rec0(it->second) + 2;
+  if (del) {
+    if (*flags & 1) ANNB_FAIL(ANNB_EINVAL, "The requested to delete element is already deleted");
+    *flags |= 1;
+    g.num_deleted++;
+  } else {
+    if (!(*flags & 1)) ANNB_FAIL(ANNB_EINVAL, "The requested to undelete element is not deleted");
+    *flags &= (uint8_t)~1;
+    g.num_deleted--;
+  }
+  h->deleted_dirty = true;
+  return ANNB_OK;
+}
+int annb_mark_deleted(annb_index_t *h, uint64_t label) {
+  ANNB_ENTER(h);
+  return set_deleted(h, label, true);
+}
+int annb_unmark_deleted(annb_index_t *h, uint64_t label) {
+  ANNB_ENTER(h);
+  return set_deleted(h, label, false);
+}
+
+int annb_element_count(annb_index_t *h, int64_t *out) {
+  if (!h || !out) ANNB_FAIL(ANNB_EINVAL, "null argument");
+  *out = h->g.inited ? h->g.count.load() : 0;
+  return ANNB_OK;
+}
+
+int annb_get_labels(annb_index_t *h, uint64_t *labels_out, int64_t cap) {
+  ANNB_ENTER(h);
+  const int64_t n = std::min<int64_t>(cap, h->g.inited ? h->g.count.load() : 0);
+  for (int64_t i = 0; i < n; i++) labels_out[i] = h->g.label((uint32_t)i);
+  return ANNB_OK;
+}
+
+int annb_get_codes(annb_index_t *h, const uint64_t *labels, int64_t n, void *codes_out) {
+  ANNB_ENTER(h);
+  HostGraph &g = h->g;
+  for (int64_t i = 0; i < n; i++) {
+    auto it = g.label_lookup.find(labels[i]);
+    if (it == g.label_lookup.end() || g.deleted(it->second)) ANNB_FAIL(ANNB_ENOTFOUND, "Label not found");
+    memcpy((uint8_t *)codes_out + (size_t)i * g.code_row_bytes, g.code(it->second), g.code_row_bytes);
+  }
+  return ANNB_OK;
+}
+
+}  // extern "C"
+
+// ---- host graph -> device walk layout ---------------------------------------------------------
+static int ensure_dev(void **p, size_t *cap, size_t bytes) {
+  if (*cap >= bytes && *p) return ANNB_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes + 256;
+    e = cudaMalloc(p, want);
+  }
+  if (e != cudaSuccess) ANNB_FAIL(ANNB_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+  *cap = want;
+  return ANNB_OK;
+}
+
+static int upload_deleted(annb_index *h) {
+  HostGraph &g = h->g;
+  const int64_t n = g.count.load();
+  const size_t words = (size_t)(n + 31) / 32 + 1;
+  std::vector<uint32_t> bm(words, 0);
+  for (int64_t i = 0; i < n; i++)
+    if (g.deleted((uint32_t)i)) bm[i >> 5] |= 1u << (i & 31);
+  ANNB_TRY(ensure_dev((void **)&h->d_deleted, &h->cap_deleted, words * 4));
+  ANNB_CUDA(cudaMemcpyAsync(h->d_deleted, bm.data(), words * 4, cudaMemcpyHostToDevice, h->stream));
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  h->gd.deleted = h->d_deleted;
+  h->deleted_dirty = false;
+  return ANNB_OK;
+}
+
+int sync_device_graph(annb_index *h) {
+  HostGraph &g = h->g;
+  if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  if (!h->dev_dirty) {
+    if (h->deleted_dirty) return upload_deleted(h);
+    return ANNB_OK;
+  }
+  const int64_t n = g.count.load();
+  GraphDev &d = h->gd;
+  memset(&d, 0, sizeof(d));
+  d.n = n;
+  d.M = h->M;
+  d.Ks = h->Ks;
+  d.code_bytes = h->code_bytes;
+  d.code_row = h->M * h->code_bytes;
+  d.maxM = g.maxM;
+  d.maxM0 = g.maxM0;
+  auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  d.code_off0 = (int)up16((size_t)4 * g.maxM0);
+  d.rec0_bytes = (int)up16((size_t)d.code_off0 + (size_t)g.maxM0 * d.code_row);
+  d.code_offu = (int)up16((size_t)4 * g.maxM);
+  d.tail_offu = (int)(((size_t)d.code_offu + (size_t)g.maxM * d.code_row + 7) / 8 * 8);
+  d.recu_bytes = (int)up16((size_t)d.tail_offu + 8);
+  d.maxlevel = g.maxlevel;
+  d.ep_node = g.enterpoint;
+  if (n == 0) {
+    h->dev_dirty = false;
+    return ANNB_OK;
+  }
+  if (g.maxlevel >= ANNB_MAX_LEVELS) ANNB_FAIL(ANNB_ELIMIT, "graph has %d levels (limit %d)", g.maxlevel + 1, ANNB_MAX_LEVELS);
+
+  // level 0: upload the raw records, then gather [links | neighbour codes] on the device
+  uint8_t *raw;
+  const size_t raw_bytes = (size_t)n * g.size_per_elem;
+  ANNB_TRY(annb_scratch(h, S_RAW0, raw_bytes, (void **)&raw));
+  ANNB_CUDA(cudaMemcpyAsync(raw, g.level0, raw_bytes, cudaMemcpyHostToDevice, h->stream));
+  ANNB_TRY(ensure_dev((void **)&h->d_rec0, &h->cap_rec0, (size_t)n * d.rec0_bytes));
+  d.rec0 = h->d_rec0;
+  ANNB_TRY(launch_pack_rec0(h, raw, n));
+
+  // labels
+  std::vector<uint64_t> labels((size_t)n);
+  uint64_t maxl = 0;
+  bool ident = true;
+  for (int64_t i = 0; i < n; i++) {
+    labels[i] = g.label((uint32_t)i);
+    maxl = std::max(maxl, labels[i]);
+    ident &= labels[i] == (uint64_t)i;
+  }
+  h->max_label = maxl;
+  h->labels_identity = ident;
+  ANNB_TRY(ensure_dev((void **)&h->d_labels, &h->cap_labels, (size_t)n * 8));
+  ANNB_CUDA(cudaMemcpyAsync(h->d_labels, labels.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  d.labels = h->d_labels;
+
+  // upper levels
+  std::vector<uint8_t> up;
+  std::vector<uint32_t> map_prev, map_cur;
+  size_t off = 0;
+  for (int l = 1; l <= g.maxlevel; l++) {
+    std::vector<uint32_t> nodes;
+    for (int64_t i = 0; i < n; i++)
+      if (g.levels[i] >= l) nodes.push_back((uint32_t)i);
+    map_cur.assign((size_t)n, 0xffffffffu);
+    for (size_t r = 0; r < nodes.size(); r++) map_cur[nodes[r]] = (uint32_t)r;
+    d.up_off[l] = off;
+    up.resize(off + nodes.size() * (size_t)d.recu_bytes, 0);
+    for (size_t r = 0; r < nodes.size(); r++) {
+      uint8_t *rec = up.data() + off + r * (size_t)d.recu_bytes;
+      const uint32_t u = nodes[r];
+      const uint8_t *ll = g.list_at(u, l);
+      uint16_t cnt;
+      memcpy(&cnt, ll, 2);
+      uint32_t *links = reinterpret_cast<uint32_t *>(rec);
+      for (int j = 0; j < g.maxM; j++) {
+        uint32_t lk = 0xffffffffu;
+        if (j < (int)cnt) {
+          uint32_t v;
+          memcpy(&v, ll + 4 + 4 * j, 4);
+          if (map_cur[v] == 0xffffffffu) ANNB_FAIL(ANNB_EINVAL, "Trying to make a link on a non-existent level");
+          lk = map_cur[v];
+          memcpy(rec + d.code_offu + (size_t)j * d.code_row, g.code(v), (size_t)d.code_row);
+        }
+        links[j] = lk;
+      }
+      uint32_t tail[2] = {u, l == 1 ? u : map_prev[u]};
+      memcpy(rec + d.tail_offu, tail, 8);
+    }
+    off += nodes.size() * (size_t)d.recu_bytes;
+    if (l == g.maxlevel) d.ep_rec = map_cur[g.enterpoint];
+    map_prev.swap(map_cur);
+  }
+  if (g.maxlevel <= 0) d.ep_rec = g.enterpoint;
+  ANNB_TRY(ensure_dev((void **)&h->d_up, &h->cap_up, std::max<size_t>(up.size(), 16)));
+  if (!up.empty()) ANNB_CUDA(cudaMemcpyAsync(h->d_up, up.data(), up.size(), cudaMemcpyHostToDevice, h->stream));
+  d.up = h->d_up;
+  memcpy(d.ep_code, g.code(g.enterpoint), (size_t)d.code_row);
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  ANNB_TRY(upload_deleted(h));
+  h->dev_dirty = false;
+  return ANNB_OK;
+}
+
+extern "C" {
+
+// ---- K3 ---------------------------------------------------------------------------------------
+int annb_search(annb_index_t *h, const float *queries, const float *tables, int in_space, int64_t B, int normalize, int k,
+                int ef, const uint64_t *filter_labels, int filter_space, int64_t n_filter, uint64_t *labels_out,
+                float *dists_out, int out_space, int64_t *stats_out) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if ((queries == nullptr) == (tables == nullptr)) ANNB_FAIL(ANNB_EINVAL, "exactly one of queries / tables must be given");
+  if (B < 0 || k <= 0 || ef <= 0 || !labels_out || !dists_out) ANNB_FAIL(ANNB_EINVAL, "bad B/k/ef/outputs");
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  ANNB_TRY(sync_device_graph(h));
+  if (B == 0) return ANNB_OK;
+  const int ef_eff = std::max(ef, k);  // hnswalg.h:1279
+  if (ef_eff > ANNB_MAX_EF) ANNB_FAIL(ANNB_ELIMIT, "max(ef, k)=%d exceeds ANNB_MAX_EF=%d", ef_eff, ANNB_MAX_EF);
+  const bool host_out = out_space != ANNB_DEVICE;
+  uint64_t *dl = labels_out;
+  float *dd = dists_out;
+  int64_t *dstats = nullptr;
+  int32_t *dfound;
+  if (host_out) {
+    ANNB_TRY(annb_scratch(h, S_OUT_L, (size_t)B * k * 8, (void **)&dl));
+    ANNB_TRY(annb_scratch(h, S_OUT_D, (size_t)B * k * 4, (void **)&dd));
+  }
+  ANNB_TRY(annb_scratch(h, S_FOUND, (size_t)B * 4, (void **)&dfound));
+  if (stats_out) {
+    if (host_out) ANNB_TRY(annb_scratch(h, S_STATS, (size_t)B * 24, (void **)&dstats));
+    else dstats = stats_out;
+  }
+  if (h->gd.n == 0) {  // empty index: searchKnn returns nothing (hnswalg.h:1240)
+    ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
+  }
+  // tables
+  const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
+  const float *dt;
+  if (tables) {
+    ANNB_TRY(stage_in(h, tables, in_space, tbytes, S_TABLES, (const void **)&dt));
+  } else {
+    float *t;
+    ANNB_TRY(annb_scratch(h, S_TABLES, tbytes, (void **)&t));
+    ANNB_TRY(build_tables(h, queries, in_space, B, normalize, t));
+    dt = t;
+  }
+  // filter
+  const uint32_t *dfilter = nullptr;
+  if (filter_labels) {
+    const uint64_t *dfl;
+    ANNB_TRY(stage_in(h, filter_labels, filter_space, (size_t)std::max<int64_t>(n_filter, 1) * 8, S_FLT_LABELS, (const void **)&dfl));
+    if (h->max_label > (uint64_t)h->gd.n * 64 + (1ull << 30))
+      ANNB_FAIL(ANNB_ELIMIT, "labels up to %llu are too sparse for the device filter bitmap", (unsigned long long)h->max_label);
+    uint32_t *by_label, *by_id;
+    ANNB_TRY(annb_scratch(h, S_FLT_BY_LABEL, ((size_t)(h->max_label >> 5) + 1) * 4, (void **)&by_label));
+    ANNB_TRY(annb_scratch(h, S_FLT_BY_ID, ((size_t)(h->gd.n + 31) / 32 + 1) * 4, (void **)&by_id));
+    ANNB_TRY(launch_filter_bitmap(h, dfl, n_filter, by_label, by_id));
+    dfilter = by_id;
+  }
+  SearchParams p;
+  memset(&p, 0, sizeof(p));
+  p.tables = dt;
+  p.B = B;
+  p.k = k;
+  p.ef = ef_eff;
+  p.filter = dfilter;
+  p.out_labels = dl;
+  p.out_dists = dd;
+  p.out_found = dfound;
+  p.out_stats = dstats;
+  const bool general = dfilter != nullptr || h->g.num_deleted > 0 || h->opt_force_general;
+  if (h->opt_timing) cudaEventRecord(h->ev[2], h->stream);
+  ANNB_TRY(launch_search(h, p, general));
+  if (h->opt_timing) cudaEventRecord(h->ev[3], h->stream);
+  // found < k anywhere?  (hnsw_bindings.cpp:342-345).  A tiny reduction on the host side of `found`.
+  int32_t *hfound;
+  ANNB_TRY(annb_pinned(h, 2, (size_t)B * 4, (void **)&hfound));
+  ANNB_CUDA(cudaMemcpyAsync(hfound, dfound, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (host_out) {
+    ANNB_CUDA(cudaMemcpyAsync(labels_out, dl, (size_t)B * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaMemcpyAsync(dists_out, dd, (size_t)B * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (stats_out) ANNB_CUDA(cudaMemcpyAsync(stats_out, dstats, (size_t)B * 24, cudaMemcpyDeviceToHost, h->stream));
+  }
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int64_t b = 0; b < B; b++)
+    if (hfound[b] < k)
+      ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
+  return ANNB_OK;
+}
+
+int annb_merge_topk(annb_index_t *h, const uint64_t *labels_gbk, const float *dists_gbk, int G, int64_t B, int k,
+                    uint64_t *labels_out, float *dists_out) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (!labels_gbk || !dists_gbk || !labels_out || !dists_out || G <= 0 || k <= 0 || B < 0) ANNB_FAIL(ANNB_EINVAL, "bad arguments");
+  return launch_merge_topk(h, labels_gbk, dists_gbk, G, B, k, labels_out, dists_out);
+}
+
+int annb_last_kernel_ms(annb_index_t *h, float *table_ms, float *search_ms, float *scan_ms) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  float v;
+  if (table_ms) *table_ms = (cudaEventElapsedTime(&v, h->ev[0], h->ev[1]) == cudaSuccess) ? v : -1.f;
+  if (search_ms) *search_ms = (cudaEventElapsedTime(&v, h->ev[2], h->ev[3]) == cudaSuccess) ? v : -1.f;
+  if (scan_ms) *scan_ms = (cudaEventElapsedTime(&v, h->ev[4], h->ev[5]) == cudaSuccess) ? v : -1.f;
+  cudaGetLastError();
+  return ANNB_OK;
+}
+
+int annb_launch_count(annb_index_t *h, int64_t *out) {
+  if (!h || !out) ANNB_FAIL(ANNB_EINVAL, "null argument");
+  *out = h->launches;
+  return ANNB_OK;
+}
+
+int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
+  ANNB_ENTER(h);
+  if (!name) ANNB_FAIL(ANNB_EINVAL, "null option name");
+  if (!strcmp(name, "warps_per_cta")) h->opt_warps_per_cta = value;
+  else if (!strcmp(name, "ctas_per_sm")) h->opt_ctas_per_sm = value;
+  else if (!strcmp(name, "force_general")) h->opt_force_general = value;
+  else if (!strcmp(name, "timing")) h->opt_timing = value;
+  else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
+  return ANNB_OK;
+}
+
+}  // extern "C"

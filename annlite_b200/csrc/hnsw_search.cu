@@ -1,0 +1,694 @@
+// hnsw_search.cu -- K3: warp-per-query HNSW walk over PQ codes (sm_100a).
+//
+// Reference semantics: HierarchicalNSW::searchKnn (include/hnswlib/hnswalg.h:1237-1295) =
+// greedy descent on levels maxlevel..1 (:1248-1274) + searchBaseLayerST (:243-329), and the
+// filtered twin searchKnnWithFilter (:1297-1361) + searchBaseLayerSTWithFilter (:332-440), with
+// the PQ distance PQLookup (include/hnswlib/space_pq.h:16-37): d = sum_m T[m][code_m], m
+// sequential from 0.f -- one lane scores one neighbour, so the fp32 sum order is the reference's.
+//
+// Two kernels:
+//  * hnsw_walk_fast     -- no deletions, no filter (the headline path).  The reference's two heaps
+//    collapse into ONE sorted list of ef entries kept in registers (WarpList): without deletions
+//    every candidate is also a top-candidate, so the candidate heap is exactly the not-yet-
+//    expanded members of the list (a candidate evicted from top_candidates has d >= lowerBound
+//    and the loop would break before expanding it, :270).  No visited set is needed either: a
+//    re-encountered node is either still in the list (dropped by an id compare) or was rejected /
+//    evicted with d >= lowerBound, and lowerBound only falls once the list is full, so it is
+//    rejected again (:306).  The walk therefore WRITES NOTHING to global memory until its k
+//    results.  Differences from the reference are confined to exact fp32 distance ties.
+//  * hnsw_walk_general  -- deletions and/or filter: follows the reference literally with a
+//    separate candidate bag and an exact visited bitmap (both per-warp scratch in global memory,
+//    L2 resident), because nodes that fail the filter are traversed but never admitted, so the
+//    single-list argument above does not hold.
+//
+// Memory layout: node record = [maxM0 links][maxM0 neighbour codes], so one
+// hop is one contiguous, coalesced read (384 B for M=8) instead of an adjacency read followed by
+// up to 32 dependent 8-byte gathers.  The per-query table (M*Ks fp32) sits in shared memory.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "annb_internal.h"
+#include "warp_list.cuh"
+
+namespace {
+
+constexpr uint32_t EMPTY_LINK = 0xffffffffu;
+constexpr uint32_t EXPANDED_BIT = 0x80000000u;
+constexpr uint32_t ID_MASK = 0x7fffffffu;
+
+// ---- code row in registers -------------------------------------------------------------------
+template <int CR>
+struct CodeWords {
+  uint32_t w[CR / 4];
+  __device__ __forceinline__ void load(const uint8_t *p) {
+    if (CR == 4) {
+      w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+    } else if (CR == 8) {
+      uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+      w[0] = t.x;
+      w[1] = t.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < CR / 16; i++) {
+        uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+        w[4 * i + 0] = t.x;
+        w[4 * i + 1] = t.y;
+        w[4 * i + 2] = t.z;
+        w[4 * i + 3] = t.w;
+      }
+    }
+  }
+};
+
+// PQLookup (space_pq.h:30-35): strictly sequential fp32 sum over subquantisers
+template <int CR, int CB>
+__device__ __forceinline__ float pq_lookup(const float *T, const CodeWords<CR> &c, int Ks) {
+  float r = 0.f;
+  constexpr int M = CR / CB;
+#pragma unroll
+  for (int m = 0; m < M; m++) {
+    uint32_t code;
+    if (CB == 1) code = (c.w[m >> 2] >> (8 * (m & 3))) & 0xffu;
+    else code = (c.w[m >> 1] >> (16 * (m & 1))) & 0xffffu;
+    r = __fadd_rn(r, T[m * Ks + code]);
+  }
+  return r;
+}
+// generic: code bytes straight from memory
+template <int CB>
+__device__ __forceinline__ float pq_lookup_mem(const float *T, const uint8_t *p, int M, int Ks) {
+  float r = 0.f;
+  for (int m = 0; m < M; m++) {
+    uint32_t code = CB == 1 ? (uint32_t)p[m] : (uint32_t)reinterpret_cast<const uint16_t *>(p)[m];
+    r = __fadd_rn(r, T[m * Ks + code]);
+  }
+  return r;
+}
+
+template <int CR, int CB>
+__device__ __forceinline__ float score(const float *T, const uint8_t *code_ptr, int M, int Ks) {
+  if (CR > 0) {
+    CodeWords<(CR > 0 ? CR : 4)> c;
+    c.load(code_ptr);
+    return pq_lookup<(CR > 0 ? CR : 4), CB>(T, c, Ks);
+  } else {
+    return pq_lookup_mem<CB>(T, code_ptr, M, Ks);
+  }
+}
+
+__device__ __forceinline__ void load_table(float *dst, const float *__restrict__ src, int TS, int lane) {
+  if ((TS & 3) == 0) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    for (int i = lane; i < (TS >> 2); i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = lane; i < TS; i += 32) dst[i] = __ldg(src + i);
+  }
+}
+
+struct Walk {
+  uint32_t node;   // node reached on level 0
+  float dist;      // its distance
+  int hops, nbrs, evals;
+};
+
+// Greedy descent maxlevel..1 (hnswalg.h:1245-1274).  After scanning one node's list the
+// reference holds the FIRST minimum among neighbours that beat curdist (strict <, sequential).
+template <int CR, int CB>
+__device__ __forceinline__ Walk descend(const GraphDev &g, const float *T, int lane) {
+  Walk w;
+  w.hops = 0;
+  w.nbrs = 0;
+  w.evals = 1;
+  w.dist = pq_lookup_mem<CB>(T, g.ep_code, g.M, g.Ks);  // dist to the entry point (:1246)
+  uint32_t rec = g.ep_rec;
+  for (int level = g.maxlevel; level > 0; level--) {
+    const uint8_t *base = g.up + g.up_off[level];
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      const uint8_t *r = base + (size_t)rec * g.recu_bytes;
+      float best = w.dist;
+      uint32_t best_link = EMPTY_LINK;
+      w.hops++;
+      for (int c0 = 0; c0 < g.maxM; c0 += 32) {
+        const int j = c0 + lane;
+        uint32_t link = j < g.maxM ? __ldg(reinterpret_cast<const uint32_t *>(r) + j) : EMPTY_LINK;
+        const bool valid = link != EMPTY_LINK;
+        float d = CUDART_INF_F;
+        if (valid) d = score<CR, CB>(T, r + g.code_offu + (size_t)j * g.code_row, g.M, g.Ks);
+        const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+        w.nbrs += nv;
+        w.evals += nv;
+        // warp argmin, first index wins ties
+        float md = d;
+        int mj = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          float od = __shfl_xor_sync(FULL_MASK, md, o);
+          int oj = __shfl_xor_sync(FULL_MASK, mj, o);
+          if (od < md || (od == md && oj < mj)) {
+            md = od;
+            mj = oj;
+          }
+        }
+        if (md < best) {
+          best = md;
+          best_link = __shfl_sync(FULL_MASK, link, mj);
+        }
+        if (nv < 32) break;
+      }
+      if (best_link != EMPTY_LINK) {
+        w.dist = best;
+        rec = best_link;
+        changed = true;
+      }
+    }
+    // step down: record index on the level below (node id when level == 1)
+    rec = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)rec * g.recu_bytes + g.tail_offu) + 1);
+  }
+  w.node = rec;
+  return w;
+}
+
+template <int EPL>
+__device__ __forceinline__ void write_results(const GraphDev &g, const SearchParams &p, int64_t q, const WarpList<EPL> &L,
+                                              int lane, int hops, int nbrs, int evals) {
+  const int k = p.k;
+  bool tie = false;
+  int found = 0;
+#pragma unroll
+  for (int e = 0; e < EPL; e++) {
+    const int pos = e * 32 + lane;
+    const bool have = L.v[e] != LIST_EMPTY_VAL && pos < k;
+    found += __popc(__ballot_sync(FULL_MASK, have));
+    // tie detection between adjacent list positions
+    float nk = __shfl_down_sync(FULL_MASK, L.k[e], 1);
+    const float first_next = (e + 1 < EPL) ? __shfl_sync(FULL_MASK, L.k[(e + 1 < EPL) ? e + 1 : e], 0) : CUDART_INF_F;
+    if (lane == 31) nk = first_next;
+    tie |= have && (pos + 1 < k) && (nk == L.k[e]);
+    if (pos < k) {
+      p.out_dists[q * k + pos] = have ? L.k[e] : CUDART_INF_F;
+      p.out_labels[q * k + pos] = have ? __ldg(g.labels + (L.v[e] & ID_MASK)) : (uint64_t)UINT64_MAX;
+    }
+  }
+  tie = __any_sync(FULL_MASK, tie);
+  if (tie) {
+    // rows must be ascending by (dist, label) (hnsw_bindings.cpp:346-351); equal distances are
+    // rare, fix them up serially
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = 1; i < found; i++) {
+        float d = p.out_dists[q * k + i];
+        uint64_t l = p.out_labels[q * k + i];
+        int j = i - 1;
+        while (j >= 0 && p.out_dists[q * k + j] == d && p.out_labels[q * k + j] > l) {
+          p.out_dists[q * k + j + 1] = p.out_dists[q * k + j];
+          p.out_labels[q * k + j + 1] = p.out_labels[q * k + j];
+          j--;
+        }
+        p.out_dists[q * k + j + 1] = d;
+        p.out_labels[q * k + j + 1] = l;
+      }
+    }
+  }
+  if (lane == 0) {
+    p.out_found[q] = found;
+    if (p.out_stats) {
+      p.out_stats[q * 3 + 0] = hops;
+      p.out_stats[q * 3 + 1] = nbrs;
+      p.out_stats[q * 3 + 2] = evals;
+    }
+  }
+}
+
+// =================================================================================================
+// fast path: no deletions, no filter
+// =================================================================================================
+template <int EPL, int CR, int CB, bool SMEM_TABLE>
+__global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int TS = g.M * g.Ks;
+  float *Ts = smem + (size_t)warp * TS;
+  const int ef = p.ef;
+
+  for (;;) {
+    unsigned qi = 0;
+    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    if (q >= p.B) break;
+    const float *T;
+    if (SMEM_TABLE) {
+      __syncwarp();
+      load_table(Ts, p.tables + q * TS, TS, lane);
+      __syncwarp();
+      T = Ts;
+    } else {
+      T = p.tables + q * TS;
+    }
+
+    Walk w = descend<CR, CB>(g, T, lane);
+    int hops = w.hops, nbrs = w.nbrs, evals = w.evals + 1;  // searchBaseLayerST re-scores the entry (:255)
+
+    WarpList<EPL> L;
+    L.clear();
+    L.insert(w.dist, w.node, ef);
+
+    for (;;) {
+      // nearest not-yet-expanded list entry == candidate_set.top() (:268)
+      int pos = -1;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        unsigned m = __ballot_sync(FULL_MASK, L.v[e] != LIST_EMPTY_VAL && !(L.v[e] & EXPANDED_BIT));
+        if (m && pos < 0) pos = e * 32 + __ffs(m) - 1;
+      }
+      if (pos < 0) break;
+      const uint32_t node = L.val_at(pos);
+#pragma unroll
+      for (int e = 0; e < EPL; e++)
+        if (e * 32 + lane == pos) L.v[e] |= EXPANDED_BIT;
+
+      const uint8_t *rec = g.rec0 + (size_t)node * g.rec0_bytes;
+      hops++;
+      for (int c0 = 0; c0 < g.maxM0; c0 += 32) {
+        const int j = c0 + lane;
+        const uint32_t link = j < g.maxM0 ? __ldg(reinterpret_cast<const uint32_t *>(rec) + j) : EMPTY_LINK;
+        const bool valid = link != EMPTY_LINK;
+        float d = CUDART_INF_F;
+        if (valid) d = score<CR, CB>(T, rec + g.code_off0 + (size_t)j * g.code_row, g.M, g.Ks);
+        const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+        nbrs += nv;
+        evals += nv;
+        float worst = L.key_at(ef - 1);  // lowerBound; +inf while the list is not full (:306)
+        unsigned mask = __ballot_sync(FULL_MASK, valid && d < worst);
+        while (mask) {
+          const int jj = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float dj = __shfl_sync(FULL_MASK, d, jj);
+          const uint32_t idj = __shfl_sync(FULL_MASK, link, jj);
+          if (!(dj < worst)) continue;
+          if (L.contains(idj, ID_MASK)) continue;  // already seen and still listed
+          L.insert(dj, idj, ef);
+          worst = L.key_at(ef - 1);
+        }
+        if (nv < 32) break;
+      }
+    }
+    write_results<EPL>(g, p, q, L, lane, hops, nbrs, evals);
+  }
+}
+
+// =================================================================================================
+// general path: deletions and/or filter (literal two-structure walk with an exact visited set)
+// =================================================================================================
+__device__ __forceinline__ uint64_t pack_cand(float d, uint32_t id) { return ((uint64_t)__float_as_uint(d) << 32) | id; }
+__device__ __forceinline__ float cand_d(uint64_t c) { return __uint_as_float((uint32_t)(c >> 32)); }
+__device__ __forceinline__ uint32_t cand_id(uint64_t c) { return (uint32_t)c; }
+
+template <int EPL, int CR, int CB, bool SMEM_TABLE>
+__global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const int has_del) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int TS = g.M * g.Ks;
+  float *Ts = smem + (size_t)warp * TS;
+  const int ef = p.ef;
+  const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  uint32_t *vis = p.visited + slot * p.visited_words;
+  uint32_t *touched = p.touched + slot * (int64_t)p.touched_cap;
+  uint64_t *bag = p.cand + slot * (int64_t)p.cand_cap;
+  const uint32_t *filter = p.filter;
+  const bool use_filter = filter != nullptr;
+
+  for (;;) {
+    unsigned qi = 0;
+    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    if (q >= p.B) break;
+    const float *T;
+    if (SMEM_TABLE) {
+      __syncwarp();
+      load_table(Ts, p.tables + q * TS, TS, lane);
+      __syncwarp();
+      T = Ts;
+    } else {
+      T = p.tables + q * TS;
+    }
+
+    Walk w = descend<CR, CB>(g, T, lane);
+    int hops = w.hops, nbrs = w.nbrs, evals = w.evals;
+
+    WarpList<EPL> L;  // top_candidates: admitted entries only
+    L.clear();
+    int topsize = 0, ncand = 0, ntouched = 0;
+    bool overflow = false;
+    float lower;
+    {
+      const uint32_t ep = w.node;
+      bool ok;
+      if (use_filter) ok = (filter[ep >> 5] >> (ep & 31)) & 1u;                    // :353-354
+      else ok = !has_del || !((g.deleted[ep >> 5] >> (ep & 31)) & 1u);             // :254
+      if (ok) {
+        evals++;
+        lower = w.dist;
+        L.insert(w.dist, ep, ef);
+        topsize = 1;
+        if (lane == 0) bag[0] = pack_cand(w.dist, ep);
+      } else {
+        lower = 3.402823466e+38f;  // std::numeric_limits<float>::max()
+        if (lane == 0) bag[0] = pack_cand(lower, ep);
+      }
+      ncand = 1;
+      if (lane == 0) {
+        vis[ep >> 5] |= 1u << (ep & 31);
+        touched[0] = ep;
+      }
+      ntouched = 1;
+      __syncwarp();
+    }
+
+    while (ncand > 0) {
+      // candidate_set.top(): nearest candidate; earliest inserted wins ties
+      float bd = CUDART_INF_F;
+      int bi = 0x7fffffff;
+      uint32_t bid = 0;
+      for (int i = lane; i < ncand; i += 32) {
+        const uint64_t c = bag[i];
+        const float d = cand_d(c);
+        if (d < bd || (d == bd && i < bi)) {
+          bd = d;
+          bi = i;
+          bid = cand_id(c);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_xor_sync(FULL_MASK, bd, o);
+        int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+        uint32_t oid = __shfl_xor_sync(FULL_MASK, bid, o);
+        if (od < bd || (od == bd && oi < bi)) {
+          bd = od;
+          bi = oi;
+          bid = oid;
+        }
+      }
+      if (use_filter) {
+        if (bd > lower) break;                                                     // :371
+      } else if (bd > lower && (topsize == ef || !has_del)) {
+        break;                                                                     // :270
+      }
+      // pop: move the last entry into the hole
+      if (lane == 0) bag[bi] = bag[ncand - 1];
+      ncand--;
+      __syncwarp();
+
+      const uint8_t *rec = g.rec0 + (size_t)bid * g.rec0_bytes;
+      hops++;
+      for (int c0 = 0; c0 < g.maxM0; c0 += 32) {
+        const int j = c0 + lane;
+        const uint32_t link = j < g.maxM0 ? __ldg(reinterpret_cast<const uint32_t *>(rec) + j) : EMPTY_LINK;
+        const bool valid = link != EMPTY_LINK;
+        const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+        nbrs += nv;
+        bool fresh = false;
+        if (valid) {
+          const uint32_t bit = 1u << (link & 31);
+          const uint32_t old = atomicOr(vis + (link >> 5), bit);  // exact visited set (:299-301)
+          fresh = !(old & bit);
+        }
+        const unsigned fmask = __ballot_sync(FULL_MASK, fresh);
+        const int nf = __popc(fmask);
+        evals += nf;
+        if (fresh) {
+          const int o = ntouched + __popc(fmask & ((1u << lane) - 1));
+          if (o < p.touched_cap) touched[o] = link;
+        }
+        ntouched += nf;
+        if (ntouched > p.touched_cap) overflow = true;
+        float d = CUDART_INF_F;
+        bool admit = false;
+        if (fresh) {
+          d = score<CR, CB>(T, rec + g.code_off0 + (size_t)j * g.code_row, g.M, g.Ks);
+          if (use_filter) admit = (filter[link >> 5] >> (link & 31)) & 1u;        // :423-426
+          else admit = !has_del || !((g.deleted[link >> 5] >> (link & 31)) & 1u);  // :314
+        }
+        // lowerBound only falls once top is full, so lanes failing now fail later too
+        unsigned mask = __ballot_sync(FULL_MASK, fresh && (topsize < ef || lower > d));
+        while (mask) {
+          const int jj = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float dj = __shfl_sync(FULL_MASK, d, jj);
+          const uint32_t idj = __shfl_sync(FULL_MASK, link, jj);
+          const bool aj = __shfl_sync(FULL_MASK, (int)admit, jj);
+          if (!(topsize < ef || lower > dj)) continue;                            // :306
+          if (ncand < p.cand_cap) {
+            if (lane == 0) bag[ncand] = pack_cand(dj, idj);
+          } else {
+            overflow = true;
+          }
+          ncand = min(ncand + 1, p.cand_cap);
+          if (aj) {
+            L.insert(dj, idj, ef);
+            topsize = min(topsize + 1, ef);
+          }
+          if (topsize > 0) lower = L.key_at(topsize - 1);                         // :320-321
+        }
+        __syncwarp();
+        if (nv < 32) break;
+      }
+    }
+    // reset the visited bits this query set
+    __syncwarp();
+    {
+      const int nt = min(ntouched, p.touched_cap);
+      for (int i = lane; i < nt; i += 32) vis[touched[i] >> 5] = 0u;
+      if (ntouched > p.touched_cap) {  // log overflowed: wipe everything
+        for (int64_t i = lane; i < p.visited_words; i += 32) vis[i] = 0u;
+      }
+    }
+    if (overflow && lane == 0) atomicExch(p.overflow_flag, 1);
+    __syncwarp();
+    write_results<EPL>(g, p, q, L, lane, hops, nbrs, evals);
+  }
+}
+
+// label list -> bitmap by internal id.  labels of the index are unique; the allowed list is
+// first marked in a bitmap over label values, then gathered by internal id.
+__global__ void mark_labels_kernel(const uint64_t *__restrict__ allowed, int64_t n, uint32_t *__restrict__ by_label,
+                                   uint64_t max_label) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t l = allowed[i];
+  if (l <= max_label) atomicOr(by_label + (l >> 5), 1u << (l & 31));
+}
+__global__ void gather_filter_kernel(const uint64_t *__restrict__ labels, int64_t n, const uint32_t *__restrict__ by_label,
+                                     uint32_t *__restrict__ by_id) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < n) {
+    uint64_t l = labels[i];
+    ok = (by_label[l >> 5] >> (l & 31)) & 1u;
+  }
+  unsigned m = __ballot_sync(FULL_MASK, ok);
+  if ((threadIdx.x & 31) == 0 && (i < n)) by_id[i >> 5] = m;
+}
+
+// level-0 walk records from the reference-layout records: [links | neighbour codes]
+__global__ void pack_rec0_kernel(const uint8_t *__restrict__ raw, int64_t n, int size_per_elem, int offset_data,
+                                 int maxM0, int code_row, int code_off0, int rec0_bytes, uint8_t *__restrict__ rec0) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t node = t / maxM0;
+  const int j = (int)(t - node * maxM0);
+  if (node >= n) return;
+  const uint8_t *src = raw + node * size_per_elem;
+  const unsigned cnt = *reinterpret_cast<const uint16_t *>(src);
+  uint8_t *dst = rec0 + node * rec0_bytes;
+  uint32_t link = EMPTY_LINK;
+  if ((unsigned)j < cnt) link = *reinterpret_cast<const uint32_t *>(src + 4 + 4 * j);
+  *reinterpret_cast<uint32_t *>(dst + 4 * j) = link;
+  uint8_t *cdst = dst + code_off0 + (size_t)j * code_row;
+  if (link != EMPTY_LINK) {
+    const uint8_t *csrc = raw + (size_t)link * size_per_elem + offset_data;
+    for (int b = 0; b < code_row; b++) cdst[b] = csrc[b];
+  } else {
+    for (int b = 0; b < code_row; b++) cdst[b] = 0;
+  }
+}
+
+struct LaunchGeom {
+  int warps, ctas_per_sm, smem_bytes;
+  bool smem_table;
+};
+
+LaunchGeom pick_geometry(annb_index *h, size_t table_bytes) {
+  int optin = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
+  LaunchGeom best{4, 1, 0, false};
+  if (table_bytes > (size_t)optin) {  // table does not fit: read it through L1/L2
+    best.warps = 8;
+    best.ctas_per_sm = 4;
+    return best;
+  }
+  int best_total = 0;
+  for (int W = 1; W <= 32; W++) {
+    size_t need = W * table_bytes;
+    if (need > (size_t)optin) break;
+    int ctas = (int)((size_t)per_sm / (need + 1024));
+    if (ctas < 1) continue;
+    ctas = std::min(ctas, 32);
+    int total = std::min(W * ctas, 32);  // beyond ~32 warps/SM the register file limits residency anyway
+    if (total > best_total) {
+      best_total = total;
+      best.warps = W;
+      best.ctas_per_sm = std::min(ctas, (32 + W - 1) / W);
+      best.smem_bytes = (int)need;
+      best.smem_table = true;
+    }
+  }
+  if (h->opt_warps_per_cta > 0 && h->opt_warps_per_cta * table_bytes <= (size_t)optin) {
+    best.warps = (int)h->opt_warps_per_cta;
+    best.smem_bytes = (int)(best.warps * table_bytes);
+    best.ctas_per_sm = std::max(1, (int)((size_t)per_sm / (best.smem_bytes + 1024)));
+    best.smem_table = true;
+  }
+  if (h->opt_ctas_per_sm > 0) best.ctas_per_sm = (int)h->opt_ctas_per_sm;
+  return best;
+}
+
+template <int EPL, int CR, int CB>
+int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
+  SearchParams p = p_in;
+  const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
+  LaunchGeom geo = pick_geometry(h, table_bytes);
+  const int threads = geo.warps * 32;
+  int has_del = h->g.num_deleted > 0;
+  int occ = geo.ctas_per_sm;
+#define ANNB_OCC(KERN)                                                                                                   \
+  do {                                                                                                                   \
+    if (geo.smem_bytes > 48 * 1024)                                                                                      \
+      ANNB_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes));                \
+    int o = 0;                                                                                                           \
+    ANNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, KERN, threads, geo.smem_bytes));                         \
+    occ = std::max(1, std::min(occ, o));                                                                                 \
+  } while (0)
+  unsigned int *counter;
+  int rc = annb_scratch(h, 4, 256, (void **)&counter);
+  if (rc) return rc;
+  ANNB_CUDA(cudaMemsetAsync(counter, 0, 8, h->stream));
+  p.work_counter = counter;
+  p.overflow_flag = reinterpret_cast<int32_t *>(counter + 1);
+  if (!general) {
+    if (geo.smem_table) {
+      ANNB_OCC((hnsw_walk_fast<EPL, CR, CB, true>));
+      int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
+      hnsw_walk_fast<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p);
+    } else {
+      ANNB_OCC((hnsw_walk_fast<EPL, CR, CB, false>));
+      int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
+      hnsw_walk_fast<EPL, CR, CB, false><<<blocks, threads, 0, h->stream>>>(h->gd, p);
+    }
+  } else {
+    if (geo.smem_table) ANNB_OCC((hnsw_walk_general<EPL, CR, CB, true>));
+    else ANNB_OCC((hnsw_walk_general<EPL, CR, CB, false>));
+    occ = std::max(1, std::min(occ, 16 / geo.warps));  // ~16 warps/SM: scratch is per slot
+    int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
+    const int64_t slots = (int64_t)blocks * geo.warps;
+    p.visited_words = (h->gd.n + 31) / 32;
+    p.touched_cap = 1 << 15;
+    p.cand_cap = 1 << 14;
+    uint32_t *vis;
+    static_assert(sizeof(unsigned int) == 4, "");
+    // scratch slot 5 keeps the visited bitmaps; they are left all-zero by every query, so they are
+    // cleared only when (re)allocated
+    size_t vis_bytes = (size_t)slots * p.visited_words * 4;
+    size_t before = h->scratch_cap[5];
+    if ((rc = annb_scratch(h, 5, vis_bytes, (void **)&vis))) return rc;
+    if (h->scratch_cap[5] != before) ANNB_CUDA(cudaMemsetAsync(vis, 0, h->scratch_cap[5], h->stream));
+    p.visited = vis;
+    if ((rc = annb_scratch(h, 6, (size_t)slots * p.touched_cap * 4, (void **)&p.touched))) return rc;
+    if ((rc = annb_scratch(h, 7, (size_t)slots * p.cand_cap * 8, (void **)&p.cand))) return rc;
+    if (geo.smem_table)
+      hnsw_walk_general<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del);
+    else
+      hnsw_walk_general<EPL, CR, CB, false><<<blocks, threads, 0, h->stream>>>(h->gd, p, has_del);
+  }
+#undef ANNB_OCC
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  if (general) {
+    int32_t flag = 0;
+    ANNB_CUDA(cudaMemcpyAsync(&flag, p.overflow_flag, 4, cudaMemcpyDeviceToHost, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+    if (flag) {
+      // visited bitmaps may be dirty after an overflow: wipe
+      cudaMemsetAsync(h->d_scratch[5], 0, h->scratch_cap[5], h->stream);
+      ANNB_FAIL(ANNB_ELIMIT, "general walk scratch overflow (candidate bag %d / visited log %d entries per query)",
+                p.cand_cap, p.touched_cap);
+    }
+  }
+  return ANNB_OK;
+}
+
+template <int EPL>
+int dispatch_code(annb_index *h, const SearchParams &p, bool general) {
+  const int cr = h->gd.code_row, cb = h->code_bytes;
+  if (cb == 1) {
+    switch (cr) {
+      case 4: return launch_walk<EPL, 4, 1>(h, p, general);
+      case 8: return launch_walk<EPL, 8, 1>(h, p, general);
+      case 16: return launch_walk<EPL, 16, 1>(h, p, general);
+      case 32: return launch_walk<EPL, 32, 1>(h, p, general);
+      default: return launch_walk<EPL, 0, 1>(h, p, general);
+    }
+  } else {
+    switch (cr) {
+      case 8: return launch_walk<EPL, 8, 2>(h, p, general);
+      case 16: return launch_walk<EPL, 16, 2>(h, p, general);
+      default: return launch_walk<EPL, 0, 2>(h, p, general);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_search(annb_index *h, const SearchParams &p, bool general) {
+  if (p.B == 0) return ANNB_OK;
+  if (p.B >= (int64_t)0xffffffffll) ANNB_FAIL(ANNB_ELIMIT, "at most 2^32-2 queries per call");
+  const int epl = (p.ef + 31) / 32;
+  if (epl <= 2) return dispatch_code<2>(h, p, general);
+  if (epl <= 4) return dispatch_code<4>(h, p, general);
+  if (epl <= 8) return dispatch_code<8>(h, p, general);
+  if (epl <= 16) return dispatch_code<16>(h, p, general);
+  ANNB_FAIL(ANNB_ELIMIT, "ef=%d exceeds ANNB_MAX_EF=%d", p.ef, ANNB_MAX_EF);
+}
+
+int launch_pack_rec0(annb_index *h, const uint8_t *d_level0_raw, int64_t n) {
+  if (n == 0) return ANNB_OK;
+  const int64_t total = n * h->gd.maxM0;
+  pack_rec0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
+      d_level0_raw, n, (int)h->g.size_per_elem, (int)h->g.offset_data, h->gd.maxM0, h->gd.code_row, h->gd.code_off0,
+      h->gd.rec0_bytes,
+      h->d_rec0);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
+int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t n_filter, uint32_t *d_by_label,
+                         uint32_t *d_by_id) {
+  const int64_t n = h->gd.n;
+  const size_t words = (size_t)(h->max_label >> 5) + 1;
+  ANNB_CUDA(cudaMemsetAsync(d_by_label, 0, words * 4, h->stream));
+  if (n_filter > 0)
+    mark_labels_kernel<<<(unsigned)((n_filter + 255) / 256), 256, 0, h->stream>>>(d_filter_labels, n_filter, d_by_label,
+                                                                               h->max_label);
+  const int64_t padded = (n + 31) / 32 * 32;
+  gather_filter_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, h->stream>>>(h->d_labels, n, d_by_label, d_by_id);
+  h->launches += 2;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
