@@ -149,7 +149,7 @@ int launch_l2_normalize(annb_index *h, float *x, int64_t B, int D) {
 int launch_adc_table(annb_index *h, const float *d_queries, int64_t B, float *d_out) {
   if (B == 0) return ANNB_OK;
   const int is_ip = h->metric != ANNB_METRIC_L2;
-  const float bias = (float)(1.0 / (double)h->Ks);
+  const float bias = h->opt_ip_raw ? 0.f : (float)(1.0 / (double)h->Ks);
   const int chunks = (h->Ks + K1_THREADS - 1) / K1_THREADS;
   int64_t done = 0;
   while (done < B) {  // gridDim.y <= 65535

@@ -170,6 +170,7 @@ struct annb_index {
   int64_t opt_ctas_per_sm = 0;     // 0 = auto
   int64_t opt_force_general = 0;   // use the general (visited + candidate heap) walk always
   int64_t opt_timing = 1;
+  int64_t opt_ip_raw = 0;          // K1 IP form without the 1/Ks bias: T = 0 - ip (pq_bind compatibility)
 };
 
 int annb_scratch(annb_index *h, int slot, size_t bytes, void **out);

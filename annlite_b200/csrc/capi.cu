@@ -866,6 +866,7 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "ctas_per_sm")) h->opt_ctas_per_sm = value;
   else if (!strcmp(name, "force_general")) h->opt_force_general = value;
   else if (!strcmp(name, "timing")) h->opt_timing = value;
+  else if (!strcmp(name, "ip_raw")) h->opt_ip_raw = value;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;
 }

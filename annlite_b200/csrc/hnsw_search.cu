@@ -227,12 +227,15 @@ __device__ __forceinline__ void write_results(const GraphDev &g, const SearchPar
 // fast path: no deletions, no filter
 // =================================================================================================
 template <int EPL, int CR, int CB, bool SMEM_TABLE>
-__global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p) {
-  extern __shared__ float smem[];
+__global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int table_stride_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   const int TS = g.M * g.Ks;
-  float *Ts = smem + (size_t)warp * TS;
+  // [nwarps x table (SMEM_TABLE only)] [nwarps x 32*EPL uint2 merge scratch]
+  float *Ts = reinterpret_cast<float *>(smem_raw + (size_t)warp * table_stride_bytes);
+  uint2 *scratch = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * 32 * EPL;
   const int ef = p.ef;
 
   for (;;) {
@@ -255,14 +258,16 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p) {
 
     WarpList<EPL> L;
     L.clear();
-    L.insert(w.dist, w.node, ef);
+    int size = 0;
+    float worst = CUDART_INF_F;  // lowerBound; +inf while the list is not full (:306)
+    L.merge(w.dist, w.node, lane == 0, ef, scratch, size, worst, ID_MASK);
 
     for (;;) {
       // nearest not-yet-expanded list entry == candidate_set.top() (:268)
       int pos = -1;
 #pragma unroll
       for (int e = 0; e < EPL; e++) {
-        unsigned m = __ballot_sync(FULL_MASK, L.v[e] != LIST_EMPTY_VAL && !(L.v[e] & EXPANDED_BIT));
+        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));  // empty slots have the bit set
         if (m && pos < 0) pos = e * 32 + __ffs(m) - 1;
       }
       if (pos < 0) break;
@@ -282,18 +287,9 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p) {
         const int nv = __popc(__ballot_sync(FULL_MASK, valid));
         nbrs += nv;
         evals += nv;
-        float worst = L.key_at(ef - 1);  // lowerBound; +inf while the list is not full (:306)
-        unsigned mask = __ballot_sync(FULL_MASK, valid && d < worst);
-        while (mask) {
-          const int jj = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float dj = __shfl_sync(FULL_MASK, d, jj);
-          const uint32_t idj = __shfl_sync(FULL_MASK, link, jj);
-          if (!(dj < worst)) continue;
-          if (L.contains(idj, ID_MASK)) continue;  // already seen and still listed
-          L.insert(dj, idj, ef);
-          worst = L.key_at(ef - 1);
-        }
+        // admission test of :306 for the whole neighbour list at once; candidates that a sequential
+        // scan would reject after lowerBound fell land beyond position ef-1 in the merge and drop out
+        L.merge(d, link, valid && d < worst, ef, scratch, size, worst, ID_MASK);
         if (nv < 32) break;
       }
     }
@@ -523,7 +519,8 @@ struct LaunchGeom {
   bool smem_table;
 };
 
-LaunchGeom pick_geometry(annb_index *h, size_t table_bytes) {
+LaunchGeom pick_geometry(annb_index *h, size_t table_bytes_in, size_t extra_per_warp) {
+  const size_t table_bytes = (table_bytes_in + 15) / 16 * 16 + extra_per_warp;
   int optin = 0, per_sm = 0;
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
@@ -531,6 +528,7 @@ LaunchGeom pick_geometry(annb_index *h, size_t table_bytes) {
   if (table_bytes > (size_t)optin) {  // table does not fit: read it through L1/L2
     best.warps = 8;
     best.ctas_per_sm = 4;
+    best.smem_bytes = (int)(best.warps * extra_per_warp);
     return best;
   }
   int best_total = 0;
@@ -563,7 +561,9 @@ template <int EPL, int CR, int CB>
 int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   SearchParams p = p_in;
   const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
-  LaunchGeom geo = pick_geometry(h, table_bytes);
+  const size_t extra = general ? 0 : (size_t)32 * EPL * sizeof(uint2);
+  LaunchGeom geo = pick_geometry(h, table_bytes, extra);
+  const int table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;
   const int threads = geo.warps * 32;
   int has_del = h->g.num_deleted > 0;
   int occ = geo.ctas_per_sm;
@@ -585,11 +585,11 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
     if (geo.smem_table) {
       ANNB_OCC((hnsw_walk_fast<EPL, CR, CB, true>));
       int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
-      hnsw_walk_fast<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p);
+      hnsw_walk_fast<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, table_stride);
     } else {
       ANNB_OCC((hnsw_walk_fast<EPL, CR, CB, false>));
       int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
-      hnsw_walk_fast<EPL, CR, CB, false><<<blocks, threads, 0, h->stream>>>(h->gd, p);
+      hnsw_walk_fast<EPL, CR, CB, false><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, table_stride);
     }
   } else {
     if (geo.smem_table) ANNB_OCC((hnsw_walk_general<EPL, CR, CB, true>));

@@ -100,4 +100,77 @@ struct WarpList {
     }
     return pos;
   }
+
+  // Merge up to 32 offered candidates (one per lane, `take` lanes offer (d, val)) into the list in
+  // ONE pass instead of 32 serial inserts.  Every candidate's final position is computed by counting
+  // (list entries <= d) + (live candidates ordered before it by (d, lane)); every list entry moves
+  // right by the number of live candidates with a strictly smaller key; the merged sequence is
+  // scattered through a per-warp shared-memory scratch (32*EPL uint2) and read back.  Ordering is
+  // identical to inserting the candidates one at a time in lane order (equal keys keep arrival
+  // order, the tail beyond `cap` falls off).  A candidate whose (key, id) already sits in the list is
+  // dropped (ids are unique per node, so an equal id implies an equal key: only equal keys are
+  // id-checked).  `size` and `worst` (key at cap-1, +inf while not full) are warp-uniform state.
+  __device__ __forceinline__ void merge(float d, uint32_t val, bool take, int cap, uint2 *scratch, int &size,
+                                        float &worst, uint32_t id_mask) {
+    const int lane = threadIdx.x & 31;
+    const unsigned offered = __ballot_sync(FULL_MASK, take);
+    if (!offered) return;
+    int shift[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) shift[e] = 0;
+    int rank = 0, base = 0;
+    unsigned live = offered, m = offered;
+    while (m) {
+      const int c = __ffs(m) - 1;
+      m &= m - 1;
+      const float dc = __shfl_sync(FULL_MASK, d, c);
+      int cnt = 0;
+      bool eq = false;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        cnt += __popc(__ballot_sync(FULL_MASK, k[e] <= dc));
+        eq |= (k[e] == dc);
+      }
+      if (__any_sync(FULL_MASK, eq)) {
+        const uint32_t idc = __shfl_sync(FULL_MASK, val, c) & id_mask;
+        bool dup = false;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) dup |= (k[e] == dc) && ((v[e] & id_mask) == idc) && (v[e] != LIST_EMPTY_VAL);
+        if (__any_sync(FULL_MASK, dup)) {
+          live &= ~(1u << c);
+          continue;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; e++) shift[e] += (k[e] > dc) ? 1 : 0;
+      if (lane == c) base = cnt;
+      rank += ((dc < d) || (dc == d && c < lane)) ? 1 : 0;
+    }
+    if (!live) return;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int np = e * 32 + lane + shift[e];
+      if (v[e] != LIST_EMPTY_VAL && np < cap) scratch[np] = make_uint2(__float_as_uint(k[e]), v[e]);
+    }
+    if ((live >> lane) & 1u) {
+      const int np = base + rank;
+      if (np < cap) scratch[np] = make_uint2(__float_as_uint(d), val);
+    }
+    size = min(size + __popc(live), cap);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int pos = e * 32 + lane;
+      if (pos < size) {
+        const uint2 t = scratch[pos];
+        k[e] = __uint_as_float(t.x);
+        v[e] = t.y;
+      } else {
+        k[e] = CUDART_INF_F;
+        v[e] = LIST_EMPTY_VAL;
+      }
+    }
+    worst = (size == cap) ? __uint_as_float(scratch[cap - 1].x) : CUDART_INF_F;
+    __syncwarp();
+  }
 };

@@ -1,0 +1,176 @@
+"""`AnnLite`: the product surface kept for the hot path -- train / index / search / search_numpy /
+delete / dump / restore on plain ndarrays (annlite/index.py:26-973 restated without docarray,
+SQLite or RocksDB, which are out of scope: SURVEY.md section 2 rows 17-19).
+
+One cell (n_cells == 1), PQ required.  `index()` accepts an ndarray (ids = running offsets, which
+is what CellTable hands out, annlite/storage/table.py:213-257) or any object with `.embeddings`
+(+ optional `.ids`).  `search()` returns `(dists, ids)` arrays; a `filter` is given as the array of
+admissible ids (what CellTable.query would yield, container.py:107-120).
+"""
+from pathlib import Path
+from typing import Optional, Union
+
+import numpy as np
+
+from .core.codec.pq import PQCodec
+from .core.index.hnsw.index import HnswIndex
+from .enums import Metric
+
+
+class AnnLite:
+    def __init__(self, n_dim: int, metric: Union[str, Metric] = 'cosine', n_cells: int = 1,
+                 n_subvectors: Optional[int] = None, n_clusters: Optional[int] = 256, n_probe: int = 16,
+                 n_components: Optional[int] = None, initial_size: Optional[int] = None,
+                 expand_step_size: int = 10240, data_path: Union[Path, str] = Path('./data'),
+                 create_if_missing: bool = True, read_only: bool = False, verbose: bool = False, device: int = 0,
+                 **kwargs):
+        if 'dim' in kwargs:
+            n_dim = kwargs.pop('dim')
+        if n_cells != 1:
+            raise NotImplementedError('n_cells > 1 (VQ cell routing) is out of scope: SURVEY.md section 2 row 15')
+        if n_components:
+            raise NotImplementedError('PCA projection is out of scope: SURVEY.md section 2 row 16')
+        if not n_subvectors:
+            raise NotImplementedError('annlite_b200 accelerates the PQ-encoded path: set n_subvectors')
+        assert n_dim % n_subvectors == 0, '"n_dim" needs to be divisible by "n_subvectors"'
+        self.n_dim, self.n_subvectors, self.n_clusters = n_dim, n_subvectors, n_clusters
+        self.n_cells, self.n_probe = 1, max(n_probe, 1)
+        self.metric = Metric.from_string(metric) if isinstance(metric, str) else metric
+        self.read_only = read_only
+        self.data_path = Path(data_path)
+        if create_if_missing:
+            self.data_path.mkdir(parents=True, exist_ok=True)
+        self._pq_codec = PQCodec(dim=n_dim, n_subvectors=n_subvectors, n_clusters=n_clusters, metric=self.metric,
+                                 device=device)
+        if self._pq_codec_path.exists():
+            self._pq_codec = PQCodec.load(self._pq_codec_path)
+        self._kwargs = dict(initial_size=initial_size, expand_step_size=expand_step_size, device=device, **kwargs)
+        self._index = None
+        self._n = 0
+        if self._pq_codec.is_trained:
+            self._make_index()
+            if self._index_path.exists():
+                self.restore()
+
+    # ---- paths ------------------------------------------------------------------------------------
+    @property
+    def _pq_codec_path(self):
+        return self.data_path / 'pq_codec.bin'
+
+    @property
+    def _index_path(self):
+        return self.data_path / 'cell_0.hnsw'
+
+    def _make_index(self):
+        self._index = HnswIndex(self.n_dim, metric=self.metric, pq_codec=self._pq_codec, **self._kwargs)
+
+    def _sanity_check(self, x):
+        assert x.ndim == 2, 'inputs must be a 2D array'
+        assert x.shape[1] == self.n_dim, \
+            f'inputs must have the same dimension as the index , got {x.shape[1]}, expected {self.n_dim}'
+        return x.shape
+
+    @property
+    def is_trained(self):
+        return self._pq_codec.is_trained
+
+    # ---- train / index ------------------------------------------------------------------------------
+    def train(self, x: 'np.ndarray', auto_save: bool = True, force_train: bool = False, **fit_kwargs):
+        """annlite/index.py:197-233."""
+        self._sanity_check(x)
+        if self.is_trained and not force_train:
+            return
+        self._pq_codec.fit(np.ascontiguousarray(x, dtype=np.float32), **fit_kwargs)
+        self._make_index()
+        if auto_save:
+            self.dump_model()
+
+    def set_codebook(self, codebooks):
+        self._pq_codec.set_codebook(codebooks)
+        self._make_index()
+
+    @staticmethod
+    def _embeddings(docs):
+        if isinstance(docs, np.ndarray):
+            return docs, None
+        x = np.asarray(docs.embeddings)
+        ids = getattr(docs, 'ids', None)
+        return x, (np.asarray(ids) if ids is not None else None)
+
+    def index(self, docs, ids=None, num_threads: int = -1, **kwargs):
+        """annlite/index.py:274-295 -> CellContainer.insert (container.py:262-308)."""
+        if self.read_only:
+            return
+        if not self.is_trained:
+            raise RuntimeError('The indexer is not trained, cannot add new documents')
+        x, doc_ids = self._embeddings(docs)
+        n, _ = self._sanity_check(x)
+        if ids is None:
+            ids = doc_ids
+        offsets = np.arange(self._n, self._n + n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        self._index.add_with_ids(x, offsets, num_threads=num_threads)
+        self._n += n
+        return offsets
+
+    # ---- search ---------------------------------------------------------------------------------------
+    def search_numpy(self, query_np: 'np.ndarray', filter=None, limit: int = 10, **kwargs):
+        """annlite/index.py:485-522: (dists (B, limit), ids (B, limit)); EUCLIDEAN distances are sqrt'ed
+        like HnswIndex.search does."""
+        if not self.is_trained:
+            raise RuntimeError('The indexer is not trained, cannot add new documents')
+        self._sanity_check(query_np)
+        indices = None
+        if filter is not None and not (isinstance(filter, dict) and not filter):
+            if isinstance(filter, dict):
+                raise NotImplementedError('attribute filters need the SQLite cell table (out of scope); '
+                                          'pass the admissible ids as an array instead')
+            indices = np.asarray(filter)
+            if indices.dtype == bool:
+                indices = np.nonzero(indices)[0]
+            indices = indices.astype(np.uint64)
+        return self._index.search_batch(query_np, limit=limit, indices=indices)
+
+    def search(self, docs, filter=None, limit: int = 10, **kwargs):
+        """annlite/index.py:334-359.  With an ndarray returns (dists, ids); with a docs object also
+        attaches `.matches = list of (id, score)` rows per query."""
+        x, _ = self._embeddings(docs)
+        dists, ids = self.search_numpy(np.ascontiguousarray(x, dtype=np.float32), filter=filter, limit=limit)
+        if not isinstance(docs, np.ndarray):
+            try:
+                docs.matches = [list(zip(i.tolist(), d.tolist())) for i, d in zip(ids, dists)]
+            except Exception:
+                pass
+        return dists, ids
+
+    def search_by_vectors(self, query_np, filter=None, limit: int = 10, **kwargs):
+        return self.search_numpy(query_np, filter=filter, limit=limit)
+
+    def delete(self, ids, **kwargs):
+        self._index.delete([int(i) for i in ids])
+
+    # ---- persistence ------------------------------------------------------------------------------------
+    def dump_model(self):
+        self._pq_codec.dump(self._pq_codec_path)
+
+    def dump_index(self):
+        self._index.dump(self._index_path)
+
+    def dump(self):
+        self.dump_model()
+        self.dump_index()
+
+    def restore(self):
+        self._index.load(self._index_path)
+        self._n = self._index.size
+
+    def close(self):
+        pass
+
+    @property
+    def index_size(self):
+        return self._index.size if self._index is not None else 0
+
+    @property
+    def stat(self):
+        return {'total_docs': self.index_size, 'index_size': self.index_size, 'n_cells': 1, 'n_dim': self.n_dim,
+                'metric': self.metric.name, 'is_trained': self.is_trained}
