@@ -227,7 +227,7 @@ __device__ __forceinline__ void write_results(const GraphDev &g, const SearchPar
 // fast path: no deletions, no filter
 // =================================================================================================
 template <int EPL, int CR, int CB, bool SMEM_TABLE>
-__global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int table_stride_bytes) {
+__global__ void hnsw_walk_chunked(const GraphDev g, const SearchParams p, const int table_stride_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -291,6 +291,214 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
         // scan would reject after lowerBound fell land beyond position ef-1 in the merge and drop out
         L.merge(d, link, valid && d < worst, ef, scratch, size, worst, ID_MASK);
         if (nv < 32) break;
+      }
+    }
+    write_results<EPL>(g, p, q, L, lane, hops, nbrs, evals);
+  }
+}
+
+// ---- v3: one neighbour chunk per node (maxM0 <= 32, the reference default M=16) ------------------
+// Software-pipelined hop: as soon as the neighbours are scored the most likely next node is known
+// (the nearest unexpanded list entry, or a new candidate that beats it), so its 384 B record is
+// requested BEFORE the merge and the DRAM round trip overlaps the merge work.  The next node is then
+// determined exactly from the merged list; a wrong guess only costs a reload.
+template <int EPL, int CR, int CB, bool SMEM_TABLE>
+__global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int table_stride_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int TS = g.M * g.Ks;
+  constexpr int CAP = 32 * EPL;
+  // [nwarps x table (SMEM_TABLE only)] [nwarps x (CAP list mirror + 32 candidate slots) uint2]
+  float *Ts = reinterpret_cast<float *>(smem_raw + (size_t)warp * table_stride_bytes);
+  uint2 *sl = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * (CAP + 32);
+  uint2 *cbuf = sl + CAP;
+  const int ef = p.ef;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  constexpr int CW = CR > 0 ? CR / 4 : 1;
+
+  for (;;) {
+    unsigned qi = 0;
+    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    if (q >= p.B) break;
+    const float *T;
+    if (SMEM_TABLE) {
+      __syncwarp();
+      load_table(Ts, p.tables + q * TS, TS, lane);
+      __syncwarp();
+      T = Ts;
+    } else {
+      T = p.tables + q * TS;
+    }
+
+    Walk w = descend<CR, CB>(g, T, lane);
+    int hops = w.hops, nbrs = w.nbrs, evals = w.evals + 1;  // searchBaseLayerST re-scores the entry (:255)
+
+    // list: registers (striped) + shared mirror; the entry node starts expanded (it is hop 0)
+    WarpList<EPL> L;
+    L.clear();
+    if (lane == 0) {
+      L.k[0] = w.dist;
+      L.v[0] = w.node | EXPANDED_BIT;
+      sl[0] = make_uint2(__float_as_uint(w.dist), w.node | EXPANDED_BIT);
+    }
+    int size = 1;
+    float worst = (ef == 1) ? w.dist : CUDART_INF_F;  // lowerBound (:306); +inf while the list is not full
+    __syncwarp();
+
+    // current record in registers
+    uint32_t link;
+    uint32_t cw[CW];
+    const uint8_t *code_ptr = nullptr;
+    auto load_record = [&](uint32_t node, uint32_t &lk, uint32_t *words, const uint8_t *&cptr) {
+      const uint8_t *rec = g.rec0 + (size_t)node * g.rec0_bytes;
+      lk = lane < g.maxM0 ? __ldg(reinterpret_cast<const uint32_t *>(rec) + lane) : EMPTY_LINK;
+      cptr = rec + g.code_off0 + (size_t)lane * g.code_row;
+      if (CR > 0 && lane < g.maxM0) {
+        CodeWords<(CR > 0 ? CR : 4)> c;
+        c.load(cptr);
+#pragma unroll
+        for (int i = 0; i < CW; i++) words[i] = c.w[i];
+      }
+    };
+    load_record(w.node, link, cw, code_ptr);
+
+    for (;;) {
+      hops++;
+      // ---- score the neighbour list (one lane = one neighbour, m sequential) ----
+      const bool valid = link != EMPTY_LINK;
+      float d = CUDART_INF_F;
+      if (valid) {
+        if (CR > 0) {
+          CodeWords<(CR > 0 ? CR : 4)> c;
+#pragma unroll
+          for (int i = 0; i < CW; i++) c.w[i] = cw[i];
+          d = pq_lookup<(CR > 0 ? CR : 4), CB>(T, c, g.Ks);
+        } else {
+          d = pq_lookup_mem<CB>(T, code_ptr, g.M, g.Ks);
+        }
+      }
+      const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+      nbrs += nv;
+      evals += nv;
+
+      // ---- nearest unexpanded entry of the current list ----
+      int pos2 = -1;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+        if (m && pos2 < 0) pos2 = e * 32 + __ffs(m) - 1;
+      }
+      uint2 e2 = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+      if (pos2 >= 0) e2 = sl[pos2];
+
+      // ---- admission (:306) for the whole list at once: rank by binary search, drop re-encounters ----
+      const bool take = valid && d < worst;
+      const unsigned offered = __ballot_sync(FULL_MASK, take);
+      unsigned live = 0;
+      int base = 0;
+      if (offered) {
+        bool dup = false;
+        if (take) {
+          int lo = 0, len = size;
+          while (len > 0) {
+            const int half = len >> 1;
+            const bool le = __uint_as_float(sl[lo + half].x) <= d;
+            lo = le ? lo + half + 1 : lo;
+            len = le ? len - half - 1 : half;
+          }
+          base = lo;  // number of list keys <= d: the candidate lands after its equals
+          for (int t = base - 1; t >= 0; t--) {  // an id can only match where the key matches
+            const uint2 x = sl[t];
+            if (__uint_as_float(x.x) != d) break;
+            if ((x.y & ID_MASK) == link) {
+              dup = true;
+              break;
+            }
+          }
+        }
+        live = __ballot_sync(FULL_MASK, take && !dup);
+      }
+
+      // ---- guess the next node and request its record now ----
+      const unsigned fm = __ballot_sync(FULL_MASK, ((live >> lane) & 1u) && d < __uint_as_float(e2.x));
+      uint32_t pred = LIST_EMPTY_VAL;
+      if (fm) pred = __shfl_sync(FULL_MASK, link, __ffs(fm) - 1);
+      else if (pos2 >= 0) pred = e2.y & ID_MASK;
+      uint32_t link_n = EMPTY_LINK;
+      uint32_t cw_n[CW];
+      const uint8_t *code_ptr_n = nullptr;
+      if (pred != LIST_EMPTY_VAL) load_record(pred, link_n, cw_n, code_ptr_n);
+
+      // ---- merge the live candidates into the list ----
+      int pos = pos2;
+      if (live) {
+        const int r = __popc(live & lt_mask);
+        const bool mine = (live >> lane) & 1u;
+        if (mine) cbuf[r] = make_uint2(__float_as_uint(d), link);
+        __syncwarp();
+        const int np_live = __popc(live);
+        int shift[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; e++) shift[e] = 0;
+        int crank = 0;
+        for (int i = 0; i < np_live; i++) {
+          const float dc = __uint_as_float(cbuf[i].x);
+#pragma unroll
+          for (int e = 0; e < EPL; e++) shift[e] += (dc < L.k[e]) ? 1 : 0;
+          crank += ((dc < d) || (dc == d && i < r)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int np = e * 32 + lane + shift[e];
+          if (L.v[e] != LIST_EMPTY_VAL && np < ef) sl[np] = make_uint2(__float_as_uint(L.k[e]), L.v[e]);
+        }
+        if (mine) {
+          const int np = base + crank;
+          if (np < ef) sl[np] = make_uint2(__float_as_uint(d), link);
+        }
+        size = min(size + np_live, ef);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int ps = e * 32 + lane;
+          if (ps < size) {
+            const uint2 t = sl[ps];
+            L.k[e] = __uint_as_float(t.x);
+            L.v[e] = t.y;
+          } else {
+            L.k[e] = CUDART_INF_F;
+            L.v[e] = LIST_EMPTY_VAL;
+          }
+        }
+        if (size == ef) worst = __uint_as_float(sl[ef - 1].x);
+        pos = -1;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+          if (m && pos < 0) pos = e * 32 + __ffs(m) - 1;
+        }
+      }
+      if (pos < 0) break;  // candidate_set exhausted (:266)
+
+      // ---- expand `pos`: flag it in both copies, take its record ----
+      const uint32_t node = sl[pos].y & ID_MASK;
+#pragma unroll
+      for (int e = 0; e < EPL; e++)
+        if (e * 32 + lane == pos) {
+          L.v[e] |= EXPANDED_BIT;
+          sl[pos].y = L.v[e];
+        }
+      __syncwarp();
+      if (node == pred) {
+        link = link_n;
+        code_ptr = code_ptr_n;
+#pragma unroll
+        for (int i = 0; i < CW; i++) cw[i] = cw_n[i];
+      } else {
+        load_record(node, link, cw, code_ptr);
       }
     }
     write_results<EPL>(g, p, q, L, lane, hops, nbrs, evals);
@@ -519,20 +727,20 @@ struct LaunchGeom {
   bool smem_table;
 };
 
-LaunchGeom pick_geometry(annb_index *h, size_t table_bytes_in, size_t extra_per_warp) {
+LaunchGeom pick_geometry(annb_index *h, size_t table_bytes_in, size_t extra_per_warp, int max_warps) {
   const size_t table_bytes = (table_bytes_in + 15) / 16 * 16 + extra_per_warp;
   int optin = 0, per_sm = 0;
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
   LaunchGeom best{4, 1, 0, false};
   if (table_bytes > (size_t)optin) {  // table does not fit: read it through L1/L2
-    best.warps = 8;
+    best.warps = std::min(8, max_warps);
     best.ctas_per_sm = 4;
     best.smem_bytes = (int)(best.warps * extra_per_warp);
     return best;
   }
   int best_total = 0;
-  for (int W = 1; W <= 32; W++) {
+  for (int W = 1; W <= max_warps; W++) {
     size_t need = W * table_bytes;
     if (need > (size_t)optin) break;
     int ctas = (int)((size_t)per_sm / (need + 1024));
@@ -547,7 +755,7 @@ LaunchGeom pick_geometry(annb_index *h, size_t table_bytes_in, size_t extra_per_
       best.smem_table = true;
     }
   }
-  if (h->opt_warps_per_cta > 0 && h->opt_warps_per_cta * table_bytes <= (size_t)optin) {
+  if (h->opt_warps_per_cta > 0 && h->opt_warps_per_cta <= max_warps && h->opt_warps_per_cta * table_bytes <= (size_t)optin) {
     best.warps = (int)h->opt_warps_per_cta;
     best.smem_bytes = (int)(best.warps * table_bytes);
     best.ctas_per_sm = std::max(1, (int)((size_t)per_sm / (best.smem_bytes + 1024)));
@@ -561,19 +769,36 @@ template <int EPL, int CR, int CB>
 int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   SearchParams p = p_in;
   const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
-  const size_t extra = general ? 0 : (size_t)32 * EPL * sizeof(uint2);
-  LaunchGeom geo = pick_geometry(h, table_bytes, extra);
-  const int table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;
-  const int threads = geo.warps * 32;
+  const bool chunked = h->gd.maxM0 > 32;
+  const size_t extra = general ? 0 : (size_t)(32 * EPL + (chunked ? 0 : 32)) * sizeof(uint2);
+  int max_warps = 32;
+  LaunchGeom geo = pick_geometry(h, table_bytes, extra, max_warps);
+  int table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;
+  int threads = geo.warps * 32;
   int has_del = h->g.num_deleted > 0;
   int occ = geo.ctas_per_sm;
+  bool fits = true;
+  // Large EPL instantiations need > 64 registers/thread: a CTA of 32 warps may not fit the register
+  // file.  ANNB_OCC asks the runtime; on 0 resident CTAs the geometry is re-picked with fewer warps.
 #define ANNB_OCC(KERN)                                                                                                   \
   do {                                                                                                                   \
-    if (geo.smem_bytes > 48 * 1024)                                                                                      \
-      ANNB_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes));                \
-    int o = 0;                                                                                                           \
-    ANNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, KERN, threads, geo.smem_bytes));                         \
-    occ = std::max(1, std::min(occ, o));                                                                                 \
+    for (;;) {                                                                                                           \
+      if (geo.smem_bytes > 48 * 1024)                                                                                    \
+        ANNB_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes));              \
+      int o = 0;                                                                                                         \
+      ANNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, KERN, threads, geo.smem_bytes));                       \
+      if (o >= 1 || max_warps == 1) {                                                                                    \
+        fits = o >= 1;                                                                                                   \
+        occ = std::max(1, std::min(occ, o));                                                                             \
+        break;                                                                                                           \
+      }                                                                                                                  \
+      max_warps = std::max(1, std::min(max_warps, geo.warps) / 2);                                                       \
+      geo = pick_geometry(h, table_bytes, extra, max_warps);                                                             \
+      table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;                                           \
+      threads = geo.warps * 32;                                                                                          \
+      occ = geo.ctas_per_sm;                                                                                             \
+    }                                                                                                                    \
+    if (!fits) ANNB_FAIL(ANNB_ELIMIT, "kernel does not fit on this device (registers/shared memory)");                   \
   } while (0)
   unsigned int *counter;
   int rc = annb_scratch(h, 4, 256, (void **)&counter);
@@ -582,15 +807,20 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   p.work_counter = counter;
   p.overflow_flag = reinterpret_cast<int32_t *>(counter + 1);
   if (!general) {
-    if (geo.smem_table) {
-      ANNB_OCC((hnsw_walk_fast<EPL, CR, CB, true>));
-      int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
-      hnsw_walk_fast<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, table_stride);
+#define ANNB_LAUNCH_FAST(KERN)                                                                                   \
+  do {                                                                                                           \
+    ANNB_OCC(KERN);                                                                                              \
+    int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);          \
+    KERN<<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, table_stride);                                \
+  } while (0)
+    if (chunked) {
+      if (geo.smem_table) ANNB_LAUNCH_FAST((hnsw_walk_chunked<EPL, CR, CB, true>));
+      else ANNB_LAUNCH_FAST((hnsw_walk_chunked<EPL, CR, CB, false>));
     } else {
-      ANNB_OCC((hnsw_walk_fast<EPL, CR, CB, false>));
-      int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
-      hnsw_walk_fast<EPL, CR, CB, false><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, table_stride);
+      if (geo.smem_table) ANNB_LAUNCH_FAST((hnsw_walk_fast<EPL, CR, CB, true>));
+      else ANNB_LAUNCH_FAST((hnsw_walk_fast<EPL, CR, CB, false>));
     }
+#undef ANNB_LAUNCH_FAST
   } else {
     if (geo.smem_table) ANNB_OCC((hnsw_walk_general<EPL, CR, CB, true>));
     else ANNB_OCC((hnsw_walk_general<EPL, CR, CB, false>));
