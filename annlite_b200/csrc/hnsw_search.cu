@@ -339,6 +339,10 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
     // list: registers (striped) + shared mirror; the entry node starts expanded (it is hop 0)
     WarpList<EPL> L;
     L.clear();
+    // the shared mirror is padded with +inf keys so the rank search below needs no bounds
+#pragma unroll
+    for (int e = 0; e < EPL; e++) sl[e * 32 + lane] = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+    __syncwarp();
     if (lane == 0) {
       L.k[0] = w.dist;
       L.v[0] = w.node | EXPANDED_BIT;
@@ -352,11 +356,15 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
     uint32_t link;
     uint32_t cw[CW];
     const uint8_t *code_ptr = nullptr;
+    const bool lane_has_slot = lane < g.maxM0;
+    const uint8_t *lane_link_base = g.rec0 + 4 * lane;
+    const uint8_t *lane_code_base = g.rec0 + g.code_off0 + (size_t)lane * g.code_row;
+    const uint32_t rec_bytes = (uint32_t)g.rec0_bytes;
     auto load_record = [&](uint32_t node, uint32_t &lk, uint32_t *words, const uint8_t *&cptr) {
-      const uint8_t *rec = g.rec0 + (size_t)node * g.rec0_bytes;
-      lk = lane < g.maxM0 ? __ldg(reinterpret_cast<const uint32_t *>(rec) + lane) : EMPTY_LINK;
-      cptr = rec + g.code_off0 + (size_t)lane * g.code_row;
-      if (CR > 0 && lane < g.maxM0) {
+      const size_t off = (size_t)node * rec_bytes;
+      lk = lane_has_slot ? __ldg(reinterpret_cast<const uint32_t *>(lane_link_base + off)) : EMPTY_LINK;
+      cptr = lane_code_base + off;
+      if (CR > 0 && lane_has_slot) {
         CodeWords<(CR > 0 ? CR : 4)> c;
         c.load(cptr);
 #pragma unroll
@@ -402,13 +410,11 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
       if (offered) {
         bool dup = false;
         if (take) {
-          int lo = 0, len = size;
-          while (len > 0) {
-            const int half = len >> 1;
-            const bool le = __uint_as_float(sl[lo + half].x) <= d;
-            lo = le ? lo + half + 1 : lo;
-            len = le ? len - half - 1 : half;
-          }
+          // branch-free lower bound over the CAP-entry (inf padded) mirror; d < worst <= key[ef-1]
+          // guarantees the count fits in [0, CAP-1]
+          int lo = 0;
+#pragma unroll
+          for (int step = CAP / 2; step >= 1; step >>= 1) lo += (__uint_as_float(sl[lo + step - 1].x) <= d) ? step : 0;
           base = lo;  // number of list keys <= d: the candidate lands after its equals
           for (int t = base - 1; t >= 0; t--) {  // an id can only match where the key matches
             const uint2 x = sl[t];
@@ -474,11 +480,14 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
           }
         }
         if (size == ef) worst = __uint_as_float(sl[ef - 1].x);
-        pos = -1;
+        // no live candidate beats the old nearest-unexpanded entry => it did not move and is still first
+        if (fm || pos2 < 0) {
+          pos = -1;
 #pragma unroll
-        for (int e = 0; e < EPL; e++) {
-          const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
-          if (m && pos < 0) pos = e * 32 + __ffs(m) - 1;
+          for (int e = 0; e < EPL; e++) {
+            const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+            if (m && pos < 0) pos = e * 32 + __ffs(m) - 1;
+          }
         }
       }
       if (pos < 0) break;  // candidate_set exhausted (:266)
@@ -513,12 +522,15 @@ __device__ __forceinline__ float cand_d(uint64_t c) { return __uint_as_float((ui
 __device__ __forceinline__ uint32_t cand_id(uint64_t c) { return (uint32_t)c; }
 
 template <int EPL, int CR, int CB, bool SMEM_TABLE>
-__global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const int has_del) {
-  extern __shared__ float smem[];
+__global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const int has_del, const int table_stride_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
   const int TS = g.M * g.Ks;
-  float *Ts = smem + (size_t)warp * TS;
+  float *Ts = reinterpret_cast<float *>(smem_raw + (size_t)warp * table_stride_bytes);
+  uint2 *scratch = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * 32 * EPL;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int ef = p.ef;
   const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   uint32_t *vis = p.visited + slot * p.visited_words;
@@ -608,6 +620,26 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
       if (lane == 0) bag[bi] = bag[ncand - 1];
       ncand--;
       __syncwarp();
+      // candidates beyond lowerBound are dead once top is full (lowerBound only falls): drop them now and
+      // then so the nearest-candidate scan stays short
+      if ((hops & 7) == 7 && topsize == ef && ncand > 64) {
+        int wpos = 0;
+        for (int b0 = 0; b0 < ncand; b0 += 32) {
+          const int i = b0 + lane;
+          uint64_t c = 0;
+          bool keep = false;
+          if (i < ncand) {
+            c = bag[i];
+            keep = !(cand_d(c) > lower);
+          }
+          const unsigned km = __ballot_sync(FULL_MASK, keep);
+          __syncwarp();
+          if (keep) bag[wpos + __popc(km & lt_mask)] = c;
+          wpos += __popc(km);
+          __syncwarp();
+        }
+        ncand = wpos;
+      }
 
       const uint8_t *rec = g.rec0 + (size_t)bid * g.rec0_bytes;
       hops++;
@@ -639,25 +671,20 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
           if (use_filter) admit = (filter[link >> 5] >> (link & 31)) & 1u;        // :423-426
           else admit = !has_del || !((g.deleted[link >> 5] >> (link & 31)) & 1u);  // :314
         }
-        // lowerBound only falls once top is full, so lanes failing now fail later too
-        unsigned mask = __ballot_sync(FULL_MASK, fresh && (topsize < ef || lower > d));
-        while (mask) {
-          const int jj = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float dj = __shfl_sync(FULL_MASK, d, jj);
-          const uint32_t idj = __shfl_sync(FULL_MASK, link, jj);
-          const bool aj = __shfl_sync(FULL_MASK, (int)admit, jj);
-          if (!(topsize < ef || lower > dj)) continue;                            // :306
-          if (ncand < p.cand_cap) {
-            if (lane == 0) bag[ncand] = pack_cand(dj, idj);
-          } else {
-            overflow = true;
-          }
-          ncand = min(ncand + 1, p.cand_cap);
-          if (aj) {
-            L.insert(dj, idj, ef);
-            topsize = min(topsize + 1, ef);
-          }
+        // Admission (:306 / :413) for the whole neighbour list at once.  lowerBound only falls once top
+        // is full, so testing against its value at the start of the list admits a superset of what the
+        // sequential scan admits; the extras have d >= the final lowerBound, are never expanded (the
+        // loop breaks first, :270 / :371) and fall off the top list in the merge -- same results.
+        const bool cand_ok = fresh && (topsize < ef || lower > d);
+        const unsigned cmask = __ballot_sync(FULL_MASK, cand_ok);
+        if (cmask) {
+          const int o = ncand + __popc(cmask & lt_mask);
+          if (cand_ok && o < p.cand_cap) bag[o] = pack_cand(d, link);
+          const int want = ncand + __popc(cmask);
+          if (want > p.cand_cap) overflow = true;
+          ncand = min(want, p.cand_cap);
+          float unused_worst;
+          L.merge(d, link, cand_ok && admit, ef, scratch, topsize, unused_worst, ID_MASK);
           if (topsize > 0) lower = L.key_at(topsize - 1);                         // :320-321
         }
         __syncwarp();
@@ -770,7 +797,7 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   SearchParams p = p_in;
   const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
   const bool chunked = h->gd.maxM0 > 32;
-  const size_t extra = general ? 0 : (size_t)(32 * EPL + (chunked ? 0 : 32)) * sizeof(uint2);
+  const size_t extra = (size_t)(32 * EPL + ((general || chunked) ? 0 : 32)) * sizeof(uint2);
   int max_warps = 32;
   LaunchGeom geo = pick_geometry(h, table_bytes, extra, max_warps);
   int table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;
@@ -842,9 +869,9 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
     if ((rc = annb_scratch(h, 6, (size_t)slots * p.touched_cap * 4, (void **)&p.touched))) return rc;
     if ((rc = annb_scratch(h, 7, (size_t)slots * p.cand_cap * 8, (void **)&p.cand))) return rc;
     if (geo.smem_table)
-      hnsw_walk_general<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del);
+      hnsw_walk_general<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del, table_stride);
     else
-      hnsw_walk_general<EPL, CR, CB, false><<<blocks, threads, 0, h->stream>>>(h->gd, p, has_del);
+      hnsw_walk_general<EPL, CR, CB, false><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del, table_stride);
   }
 #undef ANNB_OCC
   h->launches++;

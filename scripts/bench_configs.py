@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Side measurements for BASELINE.json configs[0] (C1: 10k exhaustive ADC scan) and configs[3]
+(C4: 1M cosine + 50 % filter bitmap), GPU vs the compiled reference on the same box.  Not the headline
+(bench.py is); results are committed under profiles/."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import bench  # noqa: E402
+import oracle as O  # noqa: E402
+from helpers import recall, tie_aware_rows  # noqa: E402
+from oracle import ref_driver as R  # noqa: E402
+from annlite_b200.engine import Engine  # noqa: E402
+
+
+def timeit(fn, reps=5):
+    fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))
+
+
+def c1():
+    rng = np.random.default_rng(1)
+    N, D, M, Ks, B, k = 10_000, 128, 8, 256, 1000, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    from sklearn.cluster import KMeans
+    cb = np.stack([KMeans(n_clusters=Ks, max_iter=20, n_init=1, random_state=0).fit(X[:, m * 16:(m + 1) * 16]).cluster_centers_
+                   for m in range(M)]).astype(np.float32)
+    codec = R.RefCodec(cb, 'euclidean')
+    codes = codec.encode(X)
+    e = Engine(D, M, Ks, 'euclidean')
+    e.set_codebook(cb)
+    e.set_codes(codes)
+    ids, d = e.scan_topk(queries=Q, k=k)
+    oi, od = O.scan_topk(O.adc_table(Q, cb), codes, k)
+    t_gpu = timeit(lambda: e.scan_topk(queries=Q, k=k))
+    import torch
+    Qd = torch.from_numpy(Q).cuda()
+    oi_d = torch.empty((B, k), dtype=torch.int64, device='cuda')
+    od_d = torch.empty((B, k), dtype=torch.float32, device='cuda')
+    t_dev = timeit(lambda: (e.scan_topk(queries=Qd, k=k, out_ids=oi_d, out_dists=od_d), e.sync()))
+    kms = e.last_kernel_ms()
+    # reference: PQIndex.search one query per call (annlite/core/index/pq_index.py:29-56), bounded sample
+    S = 200
+    t0 = time.perf_counter()
+    ref_ids = [R.ref_pq_linear_scan(codec, codes, Q[i], k)[1] for i in range(S)]
+    t_ref = time.perf_counter() - t0
+    ref_match = float(np.mean([set(a.tolist()) == set(b.tolist()) for a, b in zip(ref_ids, ids[:S])]))
+    return {'config': 'C1 10k x 128d, M=8, exhaustive ADC, k=10, 1000 queries',
+            'ids_exact_vs_oracle': bool(np.array_equal(ids, oi)), 'dists_bit_exact': bool(np.array_equal(d.view(np.uint32), od.view(np.uint32))),
+            'id_sets_equal_vs_reference_sample': ref_match,
+            'gpu_qps_host_buffers': B / t_gpu, 'gpu_qps_device_buffers': B / t_dev, 'scan_kernel_ms': kms['scan_ms'],
+            'table_kernel_ms': kms['table_ms'], 'reference_qps_one_query_per_call': S / t_ref,
+            'alg_bytes_per_query': N * M}
+
+
+def c4(n=1_000_000):
+    sys.argv = [sys.argv[0], '--metric', 'cosine', '--n', str(n)]
+    a = bench.parse()
+    ncores = os.cpu_count()
+    cb = bench.train_codebook(a, bench.make_base(a, 0, 10_000))
+    X = bench.make_base(a)
+    Q = bench.make_queries(a, 1)[0]
+    rng = np.random.default_rng(4)
+    allow = np.nonzero(rng.random(a.n) < 0.5)[0].astype(np.uint64)
+    e = Engine(a.dim, a.m, a.ks, 'cosine')
+    e.set_codebook(cb)
+    e.init_graph(a.n, M=a.M, ef_construction=a.efc)
+    t0 = time.time()
+    e.add_items(R.l2_normalize(X).astype(np.float32), np.arange(a.n, dtype=np.uint64), num_threads=ncores)
+    t_build = time.time() - t0
+    l, d, st = e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow, with_stats=True)
+    t_flt = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow), 3)
+    k_ms = e.last_kernel_ms()['search_ms']
+    t_plain = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2), 3)
+    # parity on the same graph: oracle port (filter semantic), bounded sample
+    S = 2000
+    g = O.Graph.from_state(e.get_graph(), a.m, a.ks)
+    tq = O.adc_table(O.l2_normalize(Q[:S]).astype(np.float32), cb, 'cosine')
+    ol, od, found = O.hnsw_search(g, tq, a.k, a.ef, filter_labels=allow)
+    verdict = tie_aware_rows(l[:S], d[:S], ol, od)
+    rel = np.abs(d[:S] - od)[l[:S] == ol] / np.maximum(np.abs(od[l[:S] == ol]), 1e-12)
+    out = {'config': f'C4 {a.n} x 128d cosine, 50% filter bitmap ({len(allow)} ids), M=8, HNSW ef=64 k=10, {len(Q)} queries',
+           'index_build_s': t_build, 'gpu_filtered_qps_host_buffers': len(Q) / t_flt, 'gpu_filtered_kernel_ms': k_ms,
+           'gpu_unfiltered_qps_host_buffers': len(Q) / t_plain, 'all_results_pass_filter': bool(np.isin(l, allow).all()),
+           'hops_per_query': float(st[:, 0].mean()), 'evals_per_query': float(st[:, 2].mean()),
+           'parity_sample': S, 'rows_exact': verdict.count('exact'), 'rows_tie': verdict.count('tie'),
+           'rows_diff': verdict.count('diff'), 'recall_vs_oracle_ids': recall(l[:S], ol),
+           'max_rel_dist_err_equal_ids': float(rel.max()) if rel.size else None}
+    # reference: knn_query_with_filter on its own (thread-order dependent) graph, bounded sample
+    if R.available() and n <= 1_000_000:
+        codec = R.RefCodec(cb, 'cosine')
+        idx = R.RefHnswIndex(codec, 'cosine', capacity=a.n, ef_construction=a.efc, ef_search=a.ef, max_connection=a.M)
+        t0 = time.time()
+        idx.add_with_ids(X, np.arange(a.n), num_threads=ncores, batch=5000)
+        out['ref_build_s'] = time.time() - t0
+        Sr = 2000
+        t0 = time.perf_counter()
+        rl, rd = idx.knn_query(Q[:Sr], a.k, num_threads=ncores, indices=allow)
+        out['reference_filtered_qps_batched'] = Sr / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for j in range(5):
+            idx.search(Q[j], limit=a.k, indices=allow)
+        out['reference_filtered_qps_one_per_call'] = 5 / (time.perf_counter() - t0)
+    return out
+
+
+if __name__ == '__main__':
+    which = sys.argv[1] if len(sys.argv) > 1 else 'c1'
+    sys.argv = sys.argv[:1]
+    print(json.dumps(c1() if which == 'c1' else c4(int(os.environ.get('C4_N', 1_000_000)))))
