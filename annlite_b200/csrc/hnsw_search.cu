@@ -97,6 +97,37 @@ __device__ __forceinline__ float score(const float *T, const uint8_t *code_ptr, 
   }
 }
 
+// ---- TMA bulk copy (cp.async.bulk -> SASS UBLKCP) + mbarrier: the 8 KB per-query table is staged
+// global -> shared by ONE instruction issued by one lane; completion is signalled on a per-warp
+// mbarrier by transaction bytes.  Needs 16-byte aligned source/destination/size.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 __device__ __forceinline__ void load_table(float *dst, const float *__restrict__ src, int TS, int lane) {
   if ((TS & 3) == 0) {
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
@@ -312,8 +343,16 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
   constexpr int CAP = 32 * EPL;
   // [nwarps x table (SMEM_TABLE only)] [nwarps x (CAP list mirror + 32 candidate slots) uint2]
   float *Ts = reinterpret_cast<float *>(smem_raw + (size_t)warp * table_stride_bytes);
-  uint2 *sl = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * (CAP + 32);
+  // [nwarps x table] [nwarps x (CAP list mirror + 32 candidate slots + 1 mbarrier) x 8 B]
+  uint2 *sl = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * (CAP + 33);
   uint2 *cbuf = sl + CAP;
+  uint64_t *tbar = reinterpret_cast<uint64_t *>(cbuf + 32);
+  const bool tma_table = SMEM_TABLE && ((TS * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.tables) & 15) == 0);
+  uint32_t tphase = 0;
+  if (tma_table) {
+    if (lane == 0) mbar_init(tbar, 1);
+    __syncwarp();
+  }
   const int ef = p.ef;
   const unsigned lt_mask = (1u << lane) - 1u;
   constexpr int CW = CR > 0 ? CR / 4 : 1;
@@ -325,9 +364,18 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
     if (q >= p.B) break;
     const float *T;
     if (SMEM_TABLE) {
-      __syncwarp();
-      load_table(Ts, p.tables + q * TS, TS, lane);
-      __syncwarp();
+      __syncwarp();  // every lane is done reading the previous query's table
+      if (tma_table) {
+        if (lane == 0) {
+          mbar_expect_tx(tbar, (uint32_t)TS * 4u);
+          bulk_g2s(Ts, p.tables + q * TS, (uint32_t)TS * 4u, tbar);
+        }
+        mbar_wait(tbar, tphase);
+        tphase ^= 1u;
+      } else {
+        load_table(Ts, p.tables + q * TS, TS, lane);
+        __syncwarp();
+      }
       T = Ts;
     } else {
       T = p.tables + q * TS;
@@ -797,7 +845,7 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   SearchParams p = p_in;
   const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
   const bool chunked = h->gd.maxM0 > 32;
-  const size_t extra = (size_t)(32 * EPL + ((general || chunked) ? 0 : 32)) * sizeof(uint2);
+  const size_t extra = (size_t)(32 * EPL + ((general || chunked) ? 0 : 33)) * sizeof(uint2);
   int max_warps = 32;
   LaunchGeom geo = pick_geometry(h, table_bytes, extra, max_warps);
   int table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;

@@ -36,8 +36,8 @@ CACHE = os.path.join(ROOT, '.index_cache')
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n', type=int, default=1_000_000)
     ap.add_argument('--dim', type=int, default=128)
@@ -128,7 +128,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -150,6 +150,20 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith('active') for r in self.rows)]
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
+
+
+def ncu_traffic_bytes():
+    """DRAM bytes per K3 launch from the committed ncu capture of this same command (profiles/)."""
+    p = os.path.join(ROOT, 'profiles', 'r01_k3_walk_ncu.txt')
+    try:
+        tot = 0.0
+        for line in open(p):
+            f = line.split()
+            if f and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                tot += float(f[1]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}[f[2]]
+        return tot or None
+    except Exception:
+        return None
 
 
 def recall_at_k(pred, truth):
@@ -283,9 +297,10 @@ def run_ours(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.05)
     ms, launches, kern_ms = timed(step_dev, a.steps, a.warmup)
-    ck = clocks.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(step_e2e, a.steps, max(3, a.warmup // 2))
+    ck = clocks.stop() if rank == 0 else None   # sampled across both timed regions (resident + e2e)
 
     total_q = B * a.steps * (1 if shard else world)
     value = total_q / (ms / 1e3)
@@ -311,9 +326,12 @@ def run_ours(a):
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         achieved = alg_bytes_launch / (k3_ms / 1e3) / 1e9
+        traffic = ncu_traffic_bytes() if (a.n == 1_000_000 and a.batch == 10_000) else None
         roof = {'bound': 'hbm', 'kernel': 'hnsw_walk_fast', 'achieved': round(achieved, 2), 'peak': peak,
                 'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s',
-                'unit': 'GB/s', 'frac': round(achieved / peak, 5), 'traffic': None,
+                'unit': 'GB/s', 'frac': round(achieved / peak, 5), 'traffic': traffic,
+                'traffic_source': 'profiles/r01_k3_walk_ncu.txt (ncu --set full of this command): dram__bytes_read.sum + dram__bytes_write.sum per launch',
+                'alg_bytes_per_launch': round(alg_bytes_launch),
                 'ms_per_launch': round(k3_ms, 4), 'alg_bytes_per_query': round(float(alg_bytes_q.mean()), 1),
                 'hops_per_query': round(float(hops.mean()), 2), 'nbrs_per_query': round(float(nbrs.mean()), 1),
                 'note': 'latency-bound pointer chase; moved bytes/query = hops*record(384B)+table(8KB)'}
@@ -409,7 +427,8 @@ def run_reference(a):
     t_build = time.time() - t0
     nb = max(1, min(a.pool, a.steps + a.warmup))
     Qh = make_queries(a, nb, rank=0)
-    S = min(a.ref_sample, a.batch)
+    # bounded sample per step so that the whole --steps/--warmup run stays within a couple of minutes
+    S = min(a.ref_sample, a.batch, max(256, 1_500_000 // max(1, a.steps + a.warmup)))
 
     def step(i):
         q = Qh[i % nb][:S]

@@ -16,9 +16,10 @@ N, D, M, KS, B = 200_000, 64, 8, 256, 4096
 @pytest.fixture(scope='module')
 def big():
     rng = np.random.default_rng(42)
-    centers = rng.standard_normal((64, D)).astype(np.float32) * 3
-    X = (centers[rng.integers(0, 64, N)] + rng.standard_normal((N, D)).astype(np.float32)).astype(np.float32)
-    Q = (centers[rng.integers(0, 64, B)] + rng.standard_normal((B, D)).astype(np.float32)).astype(np.float32)
+    # i.i.d. gaussian: continuous values, so exact fp32 distance ties (the only freedom the GPU walk
+    # takes relative to the reference) are practically absent and the checks below can be strict
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
     ds = D // M
     cb = np.stack([X[rng.choice(N, KS, replace=False), m * ds:(m + 1) * ds] for m in range(M)]).astype(np.float32)
     e = Engine(D, M, KS, 'euclidean')
