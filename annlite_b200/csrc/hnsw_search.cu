@@ -775,6 +775,12 @@ __global__ void gather_filter_kernel(const uint64_t *__restrict__ labels, int64_
   if ((threadIdx.x & 31) == 0 && (i < n)) by_id[i >> 5] = m;
 }
 
+// the reference layout's element size (4 + 4*maxM0 + code_row + 8) is not a multiple of 4 for odd
+// code rows, so its fields are read bytewise
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
 // level-0 walk records from the reference-layout records: [links | neighbour codes]
 __global__ void pack_rec0_kernel(const uint8_t *__restrict__ raw, int64_t n, int size_per_elem, int offset_data,
                                  int maxM0, int code_row, int code_off0, int rec0_bytes, uint8_t *__restrict__ rec0) {
@@ -783,10 +789,10 @@ __global__ void pack_rec0_kernel(const uint8_t *__restrict__ raw, int64_t n, int
   const int j = (int)(t - node * maxM0);
   if (node >= n) return;
   const uint8_t *src = raw + node * size_per_elem;
-  const unsigned cnt = *reinterpret_cast<const uint16_t *>(src);
+  const unsigned cnt = (unsigned)src[0] | ((unsigned)src[1] << 8);
   uint8_t *dst = rec0 + node * rec0_bytes;
   uint32_t link = EMPTY_LINK;
-  if ((unsigned)j < cnt) link = *reinterpret_cast<const uint32_t *>(src + 4 + 4 * j);
+  if ((unsigned)j < cnt) link = ld_u32_unaligned(src + 4 + 4 * j);
   *reinterpret_cast<uint32_t *>(dst + 4 * j) = link;
   uint8_t *cdst = dst + code_off0 + (size_t)j * code_row;
   if (link != EMPTY_LINK) {

@@ -1,0 +1,82 @@
+"""GPU parity over the other BASELINE.json shapes (scaled down in N so the oracle finishes in seconds):
+C3-like  D=768, M=32 (32-byte code rows), ef=128, k=100      -> EPL=4, CR=32 kernels
+C5-like  D=96,  M=16 (ds=6), ef sweep 16..256, k=10          -> CR=16 kernels
+u16 codes with M=8 (16-byte rows, Ks=300) and odd geometries -> CB=2 and the generic-row kernels
+The graph is built by the product's host builder; the checker is the oracle walking the same graph."""
+import numpy as np
+import pytest
+
+import oracle as O
+from annlite_b200.engine import Engine
+from helpers import bits, tie_aware_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def build(N, D, M, Ks, metric, seed, Mconn=16, efc=100):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((96, D)).astype(np.float32)
+    ds = D // M
+    Xi = O.l2_normalize(X).astype(np.float32) if metric == 'cosine' else X
+    # codewords sampled from the vectors that get encoded (for cosine: the normalised ones) -- a codebook
+    # far from the data would map everything to one code and turn the whole test into exact ties
+    cb = np.stack([Xi[rng.choice(N, Ks, replace=False), m * ds:(m + 1) * ds] for m in range(M)]).astype(np.float32)
+    e = Engine(D, M, Ks, metric)
+    e.set_codebook(cb)
+    e.init_graph(N, M=Mconn, ef_construction=efc)
+    e.add_items(Xi, np.arange(N, dtype=np.uint64) + 11)
+    g = O.Graph.from_state(e.get_graph(), M, Ks)
+    Qn = O.l2_normalize(O.l2_normalize(Q).astype(np.float32)).astype(np.float32) if metric == 'cosine' else Q
+    return e, g, cb, Q, Qn
+
+
+def check(e, g, cb, Qn, metric, k, ef, filt=None, strict=True):
+    # cosine: tables from host-pre-normalised queries (IP form), so the comparison stays bit-exact
+    t = O.adc_table(Qn, cb, 'inner_product' if metric == 'cosine' else metric)
+    dev_t = e.adc_table(Qn, normalize=0)
+    assert np.array_equal(bits(dev_t), bits(t))
+    l, d, st = e.search(tables=t, k=k, ef=ef, filter_labels=filt, with_stats=True)
+    ol, od, found, (hops, nbrs, evals) = O.hnsw_search(g, t, k, ef, filter_labels=filt, with_counts=True)
+    assert (found == k).all()
+    v = tie_aware_rows(l, d, ol, od)
+    assert v.count('diff') == 0, (v.count('exact'), v.count('tie'), v.count('diff'))
+    same = np.array([x == 'exact' for x in v])
+    assert np.array_equal(st[same, 0], hops[same]) and np.array_equal(st[same, 1], nbrs[same])
+
+
+def test_c3_like_m32_d768_k100():
+    e, g, cb, Q, Qn = build(6000, 768, 32, 256, 'euclidean', 3)
+    check(e, g, cb, Qn, 'euclidean', k=100, ef=128)
+    check(e, g, cb, Qn, 'euclidean', k=10, ef=64)
+    allow = (np.arange(6000, dtype=np.uint64) + 11)[::2]
+    check(e, g, cb, Qn, 'euclidean', k=20, ef=128, filt=allow)
+
+
+@pytest.mark.parametrize('ef', [16, 32, 64, 128, 256])
+def test_c5_like_m16_ds6_ef_sweep(ef):
+    e, g, cb, Q, Qn = build(20000, 96, 16, 256, 'euclidean', 5)
+    check(e, g, cb, Qn, 'euclidean', k=10, ef=ef)
+
+
+def test_u16_codes_m8_and_cosine():
+    e, g, cb, Q, Qn = build(5000, 64, 8, 300, 'cosine', 7)     # 16-byte rows of u16 codes
+    check(e, g, cb, Qn, 'cosine', k=10, ef=64)
+    e, g, cb, Q, Qn = build(4000, 40, 4, 700, 'inner_product', 8)   # 8-byte rows of u16 codes
+    check(e, g, cb, Qn, 'inner_product', k=10, ef=50)
+
+
+def test_generic_code_rows_and_wide_graph():
+    e, g, cb, Q, Qn = build(4000, 36, 6, 256, 'euclidean', 9)       # 6-byte rows -> generic kernel
+    check(e, g, cb, Qn, 'euclidean', k=10, ef=64)
+    e, g, cb, Q, Qn = build(4000, 30, 5, 400, 'euclidean', 10)      # 10-byte u16 rows -> generic kernel
+    check(e, g, cb, Qn, 'euclidean', k=5, ef=40)
+    e, g, cb, Q, Qn = build(4000, 32, 8, 256, 'euclidean', 11, Mconn=24)   # maxM0 = 48 > 32: chunked walk
+    check(e, g, cb, Qn, 'euclidean', k=10, ef=64)
+    e, g, cb, Q, Qn = build(3000, 32, 8, 256, 'euclidean', 12, Mconn=5)    # odd M: 16-byte alignment padding
+    check(e, g, cb, Qn, 'euclidean', k=10, ef=64)
+
+
+def test_big_table_not_in_shared_memory():
+    e, g, cb, Q, Qn = build(8000, 32, 8, 7400, 'euclidean', 13)    # 7400 codewords: table = 231 KB > shared memory
+    check(e, g, cb, Qn, 'euclidean', k=10, ef=64)
