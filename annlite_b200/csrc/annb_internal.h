@@ -135,6 +135,7 @@ struct annb_index {
   int dim = 0, M = 0, Ks = 0, ds = 0, code_bytes = 1;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second lane of the chunked host-buffer pipeline (annb_search)
   cudaEvent_t ev[6] = {nullptr};  // [0,1] K1, [2,3] K3, [4,5] K2
   std::mutex mu;
 
@@ -170,6 +171,7 @@ struct annb_index {
   int64_t opt_ctas_per_sm = 0;     // 0 = auto
   int64_t opt_force_general = 0;   // use the general (visited + candidate heap) walk always
   int64_t opt_timing = 1;
+  int64_t opt_chunks = 0;          // host-buffer search pipeline depth: 0 = auto, 1 = off
   int64_t opt_ip_raw = 0;          // K1 IP form without the 1/Ks bias: T = 0 - ip (pq_bind compatibility)
 };
 

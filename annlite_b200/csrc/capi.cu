@@ -139,6 +139,7 @@ int annb_create(int device, int metric, int dim, int n_subvectors, int n_cluster
   }
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
   for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
   if (e != cudaSuccess) {
     annb_set_error("CUDA error %s while creating stream/events", cudaGetErrorString(e));
@@ -169,6 +170,7 @@ int annb_destroy(annb_index_t *h) {
   if (h->d_deleted) cudaFree(h->d_deleted);
   for (int i = 0; i < 6; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return ANNB_OK;
@@ -778,6 +780,73 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   if (h->gd.n == 0) {  // empty index: searchKnn returns nothing (hnswalg.h:1240)
     ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
   }
+  // ---- host-buffer fast path: chunked two-stream pipeline -------------------------------------------
+  // H2D of chunk c+1 overlaps the walk of chunk c, the walk of chunk c+1 fills the SMs that chunk c's
+  // persistent launch leaves idle in its tail, and D2H of chunk c overlaps the walk of chunk c+1.
+  {
+    const bool plain = !filter_labels && h->g.num_deleted == 0 && !h->opt_force_general;
+    int nch = (int)h->opt_chunks;
+    if (nch == 0) nch = (B >= 32768) ? 4 : (B >= 4096 ? 2 : 1);
+    if (nch > 8) nch = 8;
+    if (queries && in_space != ANNB_DEVICE && host_out && plain && nch > 1 && B >= 2 * nch) {
+      const size_t TS = (size_t)h->M * h->Ks;
+      float *dq, *dtab;
+      unsigned int *counters;
+      int32_t *hfound;
+      ANNB_TRY(annb_scratch(h, S_QUERIES, (size_t)B * h->dim * sizeof(float), (void **)&dq));
+      ANNB_TRY(annb_scratch(h, S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
+      ANNB_TRY(annb_scratch(h, S_COUNTER, 256 * 9, (void **)&counters));
+      ANNB_TRY(annb_pinned(h, 2, (size_t)B * 4, (void **)&hfound));
+      if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
+      ANNB_CUDA(cudaStreamSynchronize(h->stream));  // scratch (re)allocation and earlier work are settled
+      cudaStream_t lanes[2] = {h->stream, h->stream2};
+      cudaStream_t saved = h->stream;
+      int rc = ANNB_OK;
+      for (int c = 0; c < nch && rc == ANNB_OK; c++) {
+        const int64_t b0 = B * c / nch, b1 = B * (c + 1) / nch, nb = b1 - b0;
+        h->stream = lanes[c & 1];
+        if (cudaMemcpyAsync(dq + b0 * h->dim, queries + b0 * h->dim, (size_t)nb * h->dim * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+          rc = ANNB_ECUDA;
+          break;
+        }
+        for (int r = 0; r < normalize && rc == ANNB_OK; r++) rc = launch_l2_normalize(h, dq + b0 * h->dim, nb, h->dim);
+        if (rc == ANNB_OK) rc = launch_adc_table(h, dq + b0 * h->dim, nb, dtab + b0 * TS);
+        if (rc != ANNB_OK) break;
+        SearchParams p;
+        memset(&p, 0, sizeof(p));
+        p.tables = dtab + b0 * TS;
+        p.B = nb;
+        p.k = k;
+        p.ef = ef_eff;
+        p.out_labels = dl + b0 * k;
+        p.out_dists = dd + b0 * k;
+        p.out_found = dfound + b0;
+        p.out_stats = dstats ? dstats + b0 * 3 : nullptr;
+        p.work_counter = counters + 64 * (c + 1);
+        if (c == 0 && h->opt_timing) cudaEventRecord(h->ev[2], h->stream);
+        rc = launch_search(h, p, false);
+        if (rc != ANNB_OK) break;
+        if (c == nch - 1 && h->opt_timing) cudaEventRecord(h->ev[3], h->stream);
+        cudaMemcpyAsync(hfound + b0, dfound + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(labels_out + b0 * k, dl + b0 * k, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(dists_out + b0 * k, dd + b0 * k, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, h->stream);
+        if (stats_out) cudaMemcpyAsync(stats_out + b0 * 3, dstats + b0 * 3, (size_t)nb * 24, cudaMemcpyDeviceToHost, h->stream);
+      }
+      h->stream = saved;
+      cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->stream2);
+      if (rc != ANNB_OK) {
+        if (rc == ANNB_ECUDA) annb_set_error("CUDA error in the chunked search pipeline: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+      }
+      if (e1 != cudaSuccess || e2 != cudaSuccess)
+        ANNB_FAIL(ANNB_ECUDA, "CUDA error %s in the chunked search pipeline", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      for (int64_t b = 0; b < B; b++)
+        if (hfound[b] < k)
+          ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
+      return ANNB_OK;
+    }
+  }
   // tables
   const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
   const float *dt;
@@ -867,6 +936,7 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "force_general")) h->opt_force_general = value;
   else if (!strcmp(name, "timing")) h->opt_timing = value;
   else if (!strcmp(name, "ip_raw")) h->opt_ip_raw = value;
+  else if (!strcmp(name, "chunks")) h->opt_chunks = value;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;
 }

@@ -881,9 +881,12 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
     }                                                                                                                    \
     if (!fits) ANNB_FAIL(ANNB_ELIMIT, "kernel does not fit on this device (registers/shared memory)");                   \
   } while (0)
-  unsigned int *counter;
-  int rc = annb_scratch(h, 4, 256, (void **)&counter);
-  if (rc) return rc;
+  unsigned int *counter = p.work_counter;  // a caller running several launches concurrently passes its own slot
+  int rc;
+  if (!counter) {
+    rc = annb_scratch(h, 4, 256, (void **)&counter);
+    if (rc) return rc;
+  }
   ANNB_CUDA(cudaMemsetAsync(counter, 0, 8, h->stream));
   p.work_counter = counter;
   p.overflow_flag = reinterpret_cast<int32_t *>(counter + 1);
