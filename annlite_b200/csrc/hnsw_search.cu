@@ -6,24 +6,30 @@
 // the PQ distance PQLookup (include/hnswlib/space_pq.h:16-37): d = sum_m T[m][code_m], m
 // sequential from 0.f -- one lane scores one neighbour, so the fp32 sum order is the reference's.
 //
-// Two kernels:
-//  * hnsw_walk_fast     -- no deletions, no filter (the headline path).  The reference's two heaps
-//    collapse into ONE sorted list of ef entries kept in registers (WarpList): without deletions
-//    every candidate is also a top-candidate, so the candidate heap is exactly the not-yet-
-//    expanded members of the list (a candidate evicted from top_candidates has d >= lowerBound
-//    and the loop would break before expanding it, :270).  No visited set is needed either: a
-//    re-encountered node is either still in the list (dropped by an id compare) or was rejected /
-//    evicted with d >= lowerBound, and lowerBound only falls once the list is full, so it is
-//    rejected again (:306).  The walk therefore WRITES NOTHING to global memory until its k
-//    results.  Differences from the reference are confined to exact fp32 distance ties.
-//  * hnsw_walk_general  -- deletions and/or filter: follows the reference literally with a
-//    separate candidate bag and an exact visited bitmap (both per-warp scratch in global memory,
-//    L2 resident), because nodes that fail the filter are traversed but never admitted, so the
-//    single-list argument above does not hold.
+// Kernels:
+//  * hnsw_walk_fast     -- no deletions, no filter, maxM0 <= 32 (the headline path).  The reference's two
+//    heaps collapse into ONE sorted list of ef entries (registers + a shared-memory mirror): without
+//    deletions every candidate is also a top-candidate, so the candidate heap is exactly the not-yet-
+//    expanded members of the list (a candidate evicted from top_candidates has d >= lowerBound and the
+//    loop would break before expanding it, :270).  No visited set is needed either: a re-encountered
+//    node is either still in the list (dropped by an id compare restricted to equal keys) or was
+//    rejected / evicted with d >= lowerBound, and lowerBound only falls once the list is full, so it is
+//    rejected again (:306).  The walk therefore WRITES NOTHING to global memory until its k results.
+//    Per hop: score all <= 32 neighbours (one lane each), rank the admitted ones by a branch-free
+//    binary search over the mirror, request the likely next node's record (overlaps the merge), merge
+//    by rank counting + scatter through the mirror, then read the true next node off the merged list.
+//    Differences from the reference are confined to exact fp32 distance ties.
+//  * hnsw_walk_chunked  -- same semantics for graphs with maxM0 > 32 (neighbour list in 32-wide chunks,
+//    WarpList::merge per chunk, no prefetch).
+//  * hnsw_walk_general  -- deletions and/or filter: follows the reference literally with a separate
+//    candidate bag (shared memory, spilling to per-warp global scratch) and an exact visited bitmap
+//    (per-warp global scratch, L2 resident), because nodes that fail the filter are traversed but never
+//    admitted, so the single-list argument above does not hold.
 //
 // Memory layout: node record = [maxM0 links][maxM0 neighbour codes], so one
 // hop is one contiguous, coalesced read (384 B for M=8) instead of an adjacency read followed by
-// up to 32 dependent 8-byte gathers.  The per-query table (M*Ks fp32) sits in shared memory.
+// up to 32 dependent 8-byte gathers.  The per-query table (M*Ks fp32) is staged into shared memory
+// by one TMA bulk copy (cp.async.bulk + mbarrier) per query.
 #include <math_constants.h>
 
 #include <algorithm>
@@ -569,6 +575,8 @@ __device__ __forceinline__ uint64_t pack_cand(float d, uint32_t id) { return ((u
 __device__ __forceinline__ float cand_d(uint64_t c) { return __uint_as_float((uint32_t)(c >> 32)); }
 __device__ __forceinline__ uint32_t cand_id(uint64_t c) { return (uint32_t)c; }
 
+constexpr int SBAG = 256;  // candidate bag entries kept in shared memory per warp (spills to global beyond)
+
 template <int EPL, int CR, int CB, bool SMEM_TABLE>
 __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const int has_del, const int table_stride_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -577,13 +585,15 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
   const int nwarps = blockDim.x >> 5;
   const int TS = g.M * g.Ks;
   float *Ts = reinterpret_cast<float *>(smem_raw + (size_t)warp * table_stride_bytes);
-  uint2 *scratch = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * 32 * EPL;
+  // [nwarps x table] [nwarps x (32*EPL merge scratch + SBAG bag) x 8 B]
+  uint2 *scratch = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * (32 * EPL + SBAG);
+  uint64_t *sbag = reinterpret_cast<uint64_t *>(scratch + 32 * EPL);
   const unsigned lt_mask = (1u << lane) - 1u;
   const int ef = p.ef;
   const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   uint32_t *vis = p.visited + slot * p.visited_words;
   uint32_t *touched = p.touched + slot * (int64_t)p.touched_cap;
-  uint64_t *bag = p.cand + slot * (int64_t)p.cand_cap;
+  uint64_t *gbag = p.cand + slot * (int64_t)p.cand_cap;
   const uint32_t *filter = p.filter;
   const bool use_filter = filter != nullptr;
 
@@ -607,7 +617,8 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
 
     WarpList<EPL> L;  // top_candidates: admitted entries only
     L.clear();
-    int topsize = 0, ncand = 0, ntouched = 0;
+    // candidate_set: an unordered bag, first SBAG entries in shared memory, the rest in global scratch
+    int topsize = 0, ns = 0, ng = 0, ntouched = 0;
     bool overflow = false;
     float lower;
     {
@@ -620,12 +631,12 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
         lower = w.dist;
         L.insert(w.dist, ep, ef);
         topsize = 1;
-        if (lane == 0) bag[0] = pack_cand(w.dist, ep);
+        if (lane == 0) sbag[0] = pack_cand(w.dist, ep);
       } else {
         lower = 3.402823466e+38f;  // std::numeric_limits<float>::max()
-        if (lane == 0) bag[0] = pack_cand(lower, ep);
+        if (lane == 0) sbag[0] = pack_cand(lower, ep);
       }
-      ncand = 1;
+      ns = 1;
       if (lane == 0) {
         vis[ep >> 5] |= 1u << (ep & 31);
         touched[0] = ep;
@@ -634,17 +645,26 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
       __syncwarp();
     }
 
-    while (ncand > 0) {
-      // candidate_set.top(): nearest candidate; earliest inserted wins ties
+    while (ns + ng > 0) {
+      // candidate_set.top(): nearest candidate (shared part, then the spilled part)
       float bd = CUDART_INF_F;
       int bi = 0x7fffffff;
       uint32_t bid = 0;
-      for (int i = lane; i < ncand; i += 32) {
-        const uint64_t c = bag[i];
+      for (int i = lane; i < ns; i += 32) {
+        const uint64_t c = sbag[i];
         const float d = cand_d(c);
         if (d < bd || (d == bd && i < bi)) {
           bd = d;
           bi = i;
+          bid = cand_id(c);
+        }
+      }
+      for (int i = lane; i < ng; i += 32) {
+        const uint64_t c = gbag[i];
+        const float d = cand_d(c);
+        if (d < bd || (d == bd && i + SBAG < bi)) {
+          bd = d;
+          bi = i + SBAG;
           bid = cand_id(c);
         }
       }
@@ -664,36 +684,60 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
       } else if (bd > lower && (topsize == ef || !has_del)) {
         break;                                                                     // :270
       }
-      // pop: move the last entry into the hole
-      if (lane == 0) bag[bi] = bag[ncand - 1];
-      ncand--;
+      // request the record now; the bag maintenance below overlaps the DRAM round trip
+      const uint8_t *rec = g.rec0 + (size_t)bid * g.rec0_bytes;
+      uint32_t link0 = (lane < g.maxM0) ? __ldg(reinterpret_cast<const uint32_t *>(rec) + lane) : EMPTY_LINK;
+      // pop: move the last entry of that part into the hole
+      if (lane == 0) {
+        if (bi < SBAG) sbag[bi] = sbag[ns - 1];
+        else gbag[bi - SBAG] = gbag[ng - 1];
+      }
+      if (bi < SBAG) ns--;
+      else ng--;
       __syncwarp();
       // candidates beyond lowerBound are dead once top is full (lowerBound only falls): drop them now and
-      // then so the nearest-candidate scan stays short
-      if ((hops & 7) == 7 && topsize == ef && ncand > 64) {
+      // then so the nearest-candidate scan stays short and the shared part does not spill
+      if (topsize == ef && ((hops & 3) == 3 || ns > SBAG - 40)) {
         int wpos = 0;
-        for (int b0 = 0; b0 < ncand; b0 += 32) {
+        for (int b0 = 0; b0 < ns; b0 += 32) {
           const int i = b0 + lane;
           uint64_t c = 0;
           bool keep = false;
-          if (i < ncand) {
-            c = bag[i];
+          if (i < ns) {
+            c = sbag[i];
             keep = !(cand_d(c) > lower);
           }
           const unsigned km = __ballot_sync(FULL_MASK, keep);
           __syncwarp();
-          if (keep) bag[wpos + __popc(km & lt_mask)] = c;
+          if (keep) sbag[wpos + __popc(km & lt_mask)] = c;
           wpos += __popc(km);
           __syncwarp();
         }
-        ncand = wpos;
+        ns = wpos;
+        if (ng > 0) {
+          wpos = 0;
+          for (int b0 = 0; b0 < ng; b0 += 32) {
+            const int i = b0 + lane;
+            uint64_t c = 0;
+            bool keep = false;
+            if (i < ng) {
+              c = gbag[i];
+              keep = !(cand_d(c) > lower);
+            }
+            const unsigned km = __ballot_sync(FULL_MASK, keep);
+            __syncwarp();
+            if (keep) gbag[wpos + __popc(km & lt_mask)] = c;
+            wpos += __popc(km);
+            __syncwarp();
+          }
+          ng = wpos;
+        }
       }
 
-      const uint8_t *rec = g.rec0 + (size_t)bid * g.rec0_bytes;
       hops++;
       for (int c0 = 0; c0 < g.maxM0; c0 += 32) {
         const int j = c0 + lane;
-        const uint32_t link = j < g.maxM0 ? __ldg(reinterpret_cast<const uint32_t *>(rec) + j) : EMPTY_LINK;
+        const uint32_t link = (c0 == 0) ? link0 : (j < g.maxM0 ? __ldg(reinterpret_cast<const uint32_t *>(rec) + j) : EMPTY_LINK);
         const bool valid = link != EMPTY_LINK;
         const int nv = __popc(__ballot_sync(FULL_MASK, valid));
         nbrs += nv;
@@ -707,7 +751,7 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
         const int nf = __popc(fmask);
         evals += nf;
         if (fresh) {
-          const int o = ntouched + __popc(fmask & ((1u << lane) - 1));
+          const int o = ntouched + __popc(fmask & lt_mask);
           if (o < p.touched_cap) touched[o] = link;
         }
         ntouched += nf;
@@ -726,11 +770,16 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
         const bool cand_ok = fresh && (topsize < ef || lower > d);
         const unsigned cmask = __ballot_sync(FULL_MASK, cand_ok);
         if (cmask) {
-          const int o = ncand + __popc(cmask & lt_mask);
-          if (cand_ok && o < p.cand_cap) bag[o] = pack_cand(d, link);
-          const int want = ncand + __popc(cmask);
-          if (want > p.cand_cap) overflow = true;
-          ncand = min(want, p.cand_cap);
+          const int cnt = __popc(cmask);
+          const int r = __popc(cmask & lt_mask);
+          if (ns + cnt <= SBAG) {
+            if (cand_ok) sbag[ns + r] = pack_cand(d, link);
+            ns += cnt;
+          } else {
+            if (cand_ok && ng + r < p.cand_cap) gbag[ng + r] = pack_cand(d, link);
+            if (ng + cnt > p.cand_cap) overflow = true;
+            ng = min(ng + cnt, p.cand_cap);
+          }
           float unused_worst;
           L.merge(d, link, cand_ok && admit, ef, scratch, topsize, unused_worst, ID_MASK);
           if (topsize > 0) lower = L.key_at(topsize - 1);                         // :320-321
@@ -851,7 +900,7 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   SearchParams p = p_in;
   const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
   const bool chunked = h->gd.maxM0 > 32;
-  const size_t extra = (size_t)(32 * EPL + ((general || chunked) ? 0 : 33)) * sizeof(uint2);
+  const size_t extra = (size_t)(32 * EPL + (general ? SBAG : (chunked ? 0 : 33))) * sizeof(uint2);
   int max_warps = 32;
   LaunchGeom geo = pick_geometry(h, table_bytes, extra, max_warps);
   int table_stride = geo.smem_table ? (int)((table_bytes + 15) / 16 * 16) : 0;
@@ -908,7 +957,6 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
   } else {
     if (geo.smem_table) ANNB_OCC((hnsw_walk_general<EPL, CR, CB, true>));
     else ANNB_OCC((hnsw_walk_general<EPL, CR, CB, false>));
-    occ = std::max(1, std::min(occ, 16 / geo.warps));  // ~16 warps/SM: scratch is per slot
     int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
     const int64_t slots = (int64_t)blocks * geo.warps;
     p.visited_words = (h->gd.n + 31) / 32;
