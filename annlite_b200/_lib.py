@@ -58,6 +58,7 @@ PROTOTYPES = {
     'annb_merge_topk': (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
     'annb_last_kernel_ms': (_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'annb_launch_count': (_int, [_vp, C.POINTER(_i64)]),
+    'annb_fallback_count': (_int, [_vp, C.POINTER(_i64)]),
     'annb_set_option': (_int, [_vp, _cp, _i64]),
 }
 

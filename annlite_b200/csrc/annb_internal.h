@@ -111,6 +111,7 @@ struct SearchParams {
   int64_t B;
   int k, ef;
   const uint32_t *filter;  // bitmap by internal id, or nullptr
+  float selectivity;       // fraction of nodes that can be admitted (filter / not deleted); sizes the flagged list
   uint64_t *out_labels;    // (B,k)
   float *out_dists;        // (B,k)
   int32_t *out_found;      // (B)
@@ -166,11 +167,13 @@ struct annb_index {
   bool labels_identity = true;     // label[i] == i for all nodes
   float last_table_ms = 0, last_search_ms = 0, last_scan_ms = 0;
   int64_t launches = 0;
+  int64_t flagged_fallbacks = 0;   // batches re-run on the bitmap walk after a flagged-list overflow
   // options
   int64_t opt_warps_per_cta = 0;   // 0 = auto
   int64_t opt_ctas_per_sm = 0;     // 0 = auto
   int64_t opt_force_general = 0;   // use the general (visited + candidate heap) walk always
   int64_t opt_timing = 1;
+  int64_t opt_flagged_epl = 0;     // force the flagged walk's list size (entries/32): testing the overflow fallback
   int64_t opt_chunks = 0;          // host-buffer search pipeline depth: 0 = auto, 1 = off
   int64_t opt_ip_raw = 0;          // K1 IP form without the 1/Ks bias: T = 0 - ip (pq_bind compatibility)
 };
@@ -185,7 +188,9 @@ int launch_scan(annb_index *h, const float *d_table, float *d_out);
 int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists);
 int launch_encode(annb_index *h, const float *d_x, int64_t n, void *d_codes);
 int launch_pack_rec0(annb_index *h, const uint8_t *d_level0_raw, int64_t n);
-int launch_search(annb_index *h, const SearchParams &p, bool general);
+// mode: 0 = fast walk (no filter, no deletions), 1 = filtered/deleted walk, kernel chosen automatically
+// (flagged single-list walk when its list fits, else the bitmap walk), 2 = bitmap walk
+int launch_search(annb_index *h, const SearchParams &p, int mode);
 int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k,
                       uint64_t *labels_out, float *dists_out);
 int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t n_filter, uint32_t *d_by_label,

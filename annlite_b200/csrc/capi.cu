@@ -883,19 +883,29 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   p.out_found = dfound;
   p.out_stats = dstats;
   const bool general = dfilter != nullptr || h->g.num_deleted > 0 || h->opt_force_general;
-  if (h->opt_timing) cudaEventRecord(h->ev[2], h->stream);
-  ANNB_TRY(launch_search(h, p, general));
-  if (h->opt_timing) cudaEventRecord(h->ev[3], h->stream);
-  // found < k anywhere?  (hnsw_bindings.cpp:342-345).  A tiny reduction on the host side of `found`.
+  if (dfilter) p.selectivity = (float)std::min<double>(1.0, (double)n_filter / (double)std::max<int64_t>(1, h->gd.n));
+  else p.selectivity = (float)(1.0 - (double)h->g.num_deleted / (double)std::max<int64_t>(1, h->gd.n));
   int32_t *hfound;
   ANNB_TRY(annb_pinned(h, 2, (size_t)B * 4, (void **)&hfound));
-  ANNB_CUDA(cudaMemcpyAsync(hfound, dfound, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (host_out) {
-    ANNB_CUDA(cudaMemcpyAsync(labels_out, dl, (size_t)B * k * 8, cudaMemcpyDeviceToHost, h->stream));
-    ANNB_CUDA(cudaMemcpyAsync(dists_out, dd, (size_t)B * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (stats_out) ANNB_CUDA(cudaMemcpyAsync(stats_out, dstats, (size_t)B * 24, cudaMemcpyDeviceToHost, h->stream));
+  int mode = general ? (h->opt_force_general == 2 ? 2 : 1) : 0;
+  for (;;) {
+    if (h->opt_timing) cudaEventRecord(h->ev[2], h->stream);
+    ANNB_TRY(launch_search(h, p, mode));
+    if (h->opt_timing) cudaEventRecord(h->ev[3], h->stream);
+    // found < k anywhere?  (hnsw_bindings.cpp:342-345).  A tiny reduction on the host side of `found`.
+    ANNB_CUDA(cudaMemcpyAsync(hfound, dfound, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (host_out) {
+      ANNB_CUDA(cudaMemcpyAsync(labels_out, dl, (size_t)B * k * 8, cudaMemcpyDeviceToHost, h->stream));
+      ANNB_CUDA(cudaMemcpyAsync(dists_out, dd, (size_t)B * k * 4, cudaMemcpyDeviceToHost, h->stream));
+      if (stats_out) ANNB_CUDA(cudaMemcpyAsync(stats_out, dstats, (size_t)B * 24, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+    bool overflowed = false;
+    for (int64_t b = 0; b < B && !overflowed; b++) overflowed = hfound[b] < 0;
+    if (!overflowed || mode == 2) break;
+    mode = 2;  // a query outgrew the flagged walk's list: redo the batch on the bitmap walk (exact, any size)
+    h->flagged_fallbacks++;
   }
-  ANNB_CUDA(cudaStreamSynchronize(h->stream));
   for (int64_t b = 0; b < B; b++)
     if (hfound[b] < k)
       ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
@@ -928,6 +938,12 @@ int annb_launch_count(annb_index_t *h, int64_t *out) {
   return ANNB_OK;
 }
 
+int annb_fallback_count(annb_index_t *h, int64_t *out) {
+  if (!h || !out) ANNB_FAIL(ANNB_EINVAL, "null argument");
+  *out = h->flagged_fallbacks;
+  return ANNB_OK;
+}
+
 int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   ANNB_ENTER(h);
   if (!name) ANNB_FAIL(ANNB_EINVAL, "null option name");
@@ -937,6 +953,8 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "timing")) h->opt_timing = value;
   else if (!strcmp(name, "ip_raw")) h->opt_ip_raw = value;
   else if (!strcmp(name, "chunks")) h->opt_chunks = value;
+  else if (!strcmp(name, "flagged_epl")) h->opt_flagged_epl = value;
+  else if (!strcmp(name, "reset_counters")) h->flagged_fallbacks = 0;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;
 }

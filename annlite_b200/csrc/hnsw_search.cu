@@ -569,7 +569,344 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
 }
 
 // =================================================================================================
-// general path: deletions and/or filter (literal two-structure walk with an exact visited set)
+// flagged path: deletions and/or filter WITHOUT a visited set or a candidate bag
+// =================================================================================================
+// Same single-list idea as hnsw_walk_fast, extended to nodes that are traversed but not admitted:
+// every evaluated node that the reference would push to candidate_set (:306 / :413) is kept in ONE
+// sorted list (capacity CAP = 32*EPL, chosen by the host from the filter's selectivity) with a PASS
+// flag (admitted to top_candidates: passes the filter / is not deleted).  lowerBound is read off the
+// list: the key of the ef-th passing entry once ef of them exist (everything behind it is dropped --
+// those candidates have d >= lowerBound and are never expanded, :270 / :371), else the key of the last
+// passing entry, else FLT_MAX -- exactly the values top_candidates.top() takes in the reference.
+// While fewer than ef entries pass nothing is dropped, which is what makes the walk exact without a
+// visited set: a re-encountered node is either still listed (id compare on equal keys) or was dropped
+// with d >= a lowerBound that has only fallen since.  If the list would overflow its capacity the
+// query is flagged (found = -1) and the host re-runs the batch on the bitmap kernel below.
+constexpr uint32_t PASS_BIT = 0x40000000u;
+constexpr uint32_t ID_MASK30 = 0x3fffffffu;
+
+template <int EPL, int CR, int CB>
+__global__ void hnsw_walk_flagged(const GraphDev g, const SearchParams p, const int has_del, const int table_stride_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int TS = g.M * g.Ks;
+  constexpr int CAP = 32 * EPL;
+  float *Ts = reinterpret_cast<float *>(smem_raw + (size_t)warp * table_stride_bytes);
+  uint2 *sl = reinterpret_cast<uint2 *>(smem_raw + (size_t)nwarps * table_stride_bytes) + (size_t)warp * (CAP + 33);
+  uint2 *cbuf = sl + CAP;
+  uint64_t *tbar = reinterpret_cast<uint64_t *>(cbuf + 32);
+  const bool tma_table = ((TS * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.tables) & 15) == 0);
+  uint32_t tphase = 0;
+  if (tma_table) {
+    if (lane == 0) mbar_init(tbar, 1);
+    __syncwarp();
+  }
+  const int ef = p.ef;
+  const int k = p.k;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned le_mask = lt_mask | (1u << lane);
+  constexpr int CW = CR / 4;
+  const uint32_t *filter = p.filter;
+  const bool use_filter = filter != nullptr;
+  const uint32_t *delbits = g.deleted;
+  auto passes = [&](uint32_t id) -> bool {
+    if (use_filter) return (__ldg(filter + (id >> 5)) >> (id & 31)) & 1u;   // :353-354, :423-426
+    return !((__ldg(delbits + (id >> 5)) >> (id & 31)) & 1u);              // :254, :314
+  };
+  const float FLT_MAX_ = 3.402823466e+38f;
+
+  for (;;) {
+    unsigned qi = 0;
+    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
+    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    if (q >= p.B) break;
+    __syncwarp();
+    if (tma_table) {
+      if (lane == 0) {
+        mbar_expect_tx(tbar, (uint32_t)TS * 4u);
+        bulk_g2s(Ts, p.tables + q * TS, (uint32_t)TS * 4u, tbar);
+      }
+      mbar_wait(tbar, tphase);
+      tphase ^= 1u;
+    } else {
+      load_table(Ts, p.tables + q * TS, TS, lane);
+      __syncwarp();
+    }
+    const float *T = Ts;
+
+    Walk w = descend<CR, CB>(g, T, lane);
+    int hops = w.hops, nbrs = w.nbrs, evals = w.evals + 1;
+
+    WarpList<EPL> L;
+    L.clear();
+#pragma unroll
+    for (int e = 0; e < EPL; e++) sl[e * 32 + lane] = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+    __syncwarp();
+    const bool ep_pass = passes(w.node);
+    const uint32_t ep_val = w.node | EXPANDED_BIT | (ep_pass ? PASS_BIT : 0u);
+    if (lane == 0) {
+      L.k[0] = w.dist;
+      L.v[0] = ep_val;
+      sl[0] = make_uint2(__float_as_uint(w.dist), ep_val);
+    }
+    int size = 1, npass = ep_pass ? 1 : 0;
+    float lb = ep_pass ? w.dist : FLT_MAX_;   // lowerBound of the reference (:256 / :260)
+    bool aborted = false;
+    __syncwarp();
+
+    uint32_t link;
+    uint32_t cw[CW];
+    const bool lane_has_slot = lane < g.maxM0;
+    const uint8_t *lane_link_base = g.rec0 + 4 * lane;
+    const uint8_t *lane_code_base = g.rec0 + g.code_off0 + (size_t)lane * g.code_row;
+    const uint32_t rec_bytes = (uint32_t)g.rec0_bytes;
+    auto load_record = [&](uint32_t node, uint32_t &lk, uint32_t *words) {
+      const size_t off = (size_t)node * rec_bytes;
+      lk = lane_has_slot ? __ldg(reinterpret_cast<const uint32_t *>(lane_link_base + off)) : EMPTY_LINK;
+      if (lane_has_slot) {
+        CodeWords<CR> c;
+        c.load(lane_code_base + off);
+#pragma unroll
+        for (int i = 0; i < CW; i++) words[i] = c.w[i];
+      }
+    };
+    load_record(w.node, link, cw);
+
+    for (;;) {
+      hops++;
+      const bool valid = link != EMPTY_LINK;
+      float d = CUDART_INF_F;
+      bool pf = false;
+      if (valid) {
+        pf = passes(link);
+        CodeWords<CR> c;
+#pragma unroll
+        for (int i = 0; i < CW; i++) c.w[i] = cw[i];
+        d = pq_lookup<CR, CB>(T, c, g.Ks);
+      }
+      const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+      nbrs += nv;
+      evals += nv;
+
+      int pos2 = -1;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+        if (m && pos2 < 0) pos2 = e * 32 + __ffs(m) - 1;
+      }
+      uint2 e2 = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+      if (pos2 >= 0) e2 = sl[pos2];
+
+      // admission to candidate_set: top_candidates.size() < ef || lowerBound > dist (:306 / :413)
+      const bool take = valid && (npass < ef || d < lb);
+      const unsigned offered = __ballot_sync(FULL_MASK, take);
+      unsigned live = 0;
+      int base = 0;
+      if (offered) {
+        bool dup = false;
+        if (take) {
+          int lo = 0;
+#pragma unroll
+          for (int step = CAP / 2; step >= 1; step >>= 1) lo += (__uint_as_float(sl[lo + step - 1].x) <= d) ? step : 0;
+          base = lo;
+          for (int t = base - 1; t >= 0; t--) {
+            const uint2 x = sl[t];
+            if (__uint_as_float(x.x) != d) break;
+            if ((x.y & ID_MASK30) == link) {
+              dup = true;
+              break;
+            }
+          }
+        }
+        live = __ballot_sync(FULL_MASK, take && !dup);
+      }
+      const int np_live = __popc(live);
+      if (size + np_live > CAP) {  // capacity chosen by the host was too small for this query
+        aborted = true;
+        break;
+      }
+
+      const unsigned fm = __ballot_sync(FULL_MASK, ((live >> lane) & 1u) && d < __uint_as_float(e2.x));
+      uint32_t pred = LIST_EMPTY_VAL;
+      if (fm) pred = __shfl_sync(FULL_MASK, link, __ffs(fm) - 1);
+      else if (pos2 >= 0) pred = e2.y & ID_MASK30;
+      uint32_t link_n = EMPTY_LINK;
+      uint32_t cw_n[CW];
+      if (pred != LIST_EMPTY_VAL) load_record(pred, link_n, cw_n);
+
+      int pos = pos2;
+      if (live) {
+        const int r = __popc(live & lt_mask);
+        const bool mine = (live >> lane) & 1u;
+        const uint32_t myval = link | (pf ? PASS_BIT : 0u);
+        if (mine) cbuf[r] = make_uint2(__float_as_uint(d), myval);
+        __syncwarp();
+        int shift[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; e++) shift[e] = 0;
+        int crank = 0;
+        for (int i = 0; i < np_live; i++) {
+          const float dc = __uint_as_float(cbuf[i].x);
+#pragma unroll
+          for (int e = 0; e < EPL; e++) shift[e] += (dc < L.k[e]) ? 1 : 0;
+          crank += ((dc < d) || (dc == d && i < r)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int np = e * 32 + lane + shift[e];
+          if (L.v[e] != LIST_EMPTY_VAL) sl[np] = make_uint2(__float_as_uint(L.k[e]), L.v[e]);
+        }
+        if (mine) sl[base + crank] = make_uint2(__float_as_uint(d), myval);
+        const int merged = size + np_live;
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int ps = e * 32 + lane;
+          if (ps < merged) {
+            const uint2 t = sl[ps];
+            L.k[e] = __uint_as_float(t.x);
+            L.v[e] = t.y;
+          } else {
+            L.k[e] = CUDART_INF_F;
+            L.v[e] = LIST_EMPTY_VAL;
+          }
+        }
+        // ---- lowerBound = top_candidates.top() (:320-321) read off the list; drop what lies beyond it ----
+        unsigned pm[EPL];
+        int total = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          pm[e] = __ballot_sync(FULL_MASK, L.v[e] != LIST_EMPTY_VAL && (L.v[e] & PASS_BIT));
+          total += __popc(pm[e]);
+        }
+        size = merged;
+        if (total >= ef) {
+          int cum = 0, P = -1;
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const int c = __popc(pm[e]);
+            if (P < 0 && cum + c >= ef) {
+              const int need = ef - cum;
+              const unsigned hit = __ballot_sync(FULL_MASK, ((pm[e] >> lane) & 1u) && __popc(pm[e] & le_mask) == need);
+              P = e * 32 + __ffs(hit) - 1;
+            }
+            cum += c;
+          }
+          const int newsize = P + 1;
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const int ps = e * 32 + lane;
+            if (ps >= newsize && ps < merged) {
+              L.k[e] = CUDART_INF_F;
+              L.v[e] = LIST_EMPTY_VAL;
+              sl[ps] = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+            }
+          }
+          size = newsize;
+          npass = ef;
+          lb = __uint_as_float(sl[P].x);
+        } else {
+          npass = total;
+          if (total > 0) {
+            int plast = -1;
+#pragma unroll
+            for (int e = EPL - 1; e >= 0; e--)
+              if (plast < 0 && pm[e]) plast = e * 32 + 31 - __clz(pm[e]);
+            lb = __uint_as_float(sl[plast].x);
+          }
+        }
+        __syncwarp();
+        pos = -1;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+          if (m && pos < 0) pos = e * 32 + __ffs(m) - 1;
+        }
+      }
+      if (pos < 0) break;
+      const uint2 nx = sl[pos];
+      const float nkey = __uint_as_float(nx.x);
+      if (use_filter) {
+        if (nkey > lb) break;                                                      // :371
+      } else if (nkey > lb && (npass == ef || !has_del)) {
+        break;                                                                     // :270
+      }
+      const uint32_t node = nx.y & ID_MASK30;
+#pragma unroll
+      for (int e = 0; e < EPL; e++)
+        if (e * 32 + lane == pos) {
+          L.v[e] |= EXPANDED_BIT;
+          sl[pos].y = L.v[e];
+        }
+      __syncwarp();
+      if (node == pred) {
+        link = link_n;
+#pragma unroll
+        for (int i = 0; i < CW; i++) cw[i] = cw_n[i];
+      } else {
+        load_record(node, link, cw);
+      }
+    }
+
+    // ---- results: the first k passing entries, ascending (dist, label) ----
+    if (aborted) {
+      if (lane == 0) p.out_found[q] = -1;
+      continue;
+    }
+    int cum = 0;
+    bool tie = false;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const bool pass = L.v[e] != LIST_EMPTY_VAL && (L.v[e] & PASS_BIT);
+      const unsigned m = __ballot_sync(FULL_MASK, pass);
+      const int r = cum + __popc(m & lt_mask);
+      if (pass && r < k) {
+        p.out_dists[q * k + r] = L.k[e];
+        p.out_labels[q * k + r] = __ldg(g.labels + (L.v[e] & ID_MASK30));
+      }
+      float nk = __shfl_down_sync(FULL_MASK, L.k[e], 1);
+      const float first_next = (e + 1 < EPL) ? __shfl_sync(FULL_MASK, L.k[(e + 1 < EPL) ? e + 1 : e], 0) : CUDART_INF_F;
+      if (lane == 31) nk = first_next;
+      tie |= (L.v[e] != LIST_EMPTY_VAL) && (nk == L.k[e]);
+      cum += __popc(m);
+    }
+    const int found = min(cum, k);
+    for (int r = found + lane; r < k; r += 32) {
+      p.out_dists[q * k + r] = CUDART_INF_F;
+      p.out_labels[q * k + r] = (uint64_t)UINT64_MAX;
+    }
+    if (__any_sync(FULL_MASK, tie)) {
+      __syncwarp();
+      if (lane == 0) {
+        for (int i = 1; i < found; i++) {
+          float dd = p.out_dists[q * k + i];
+          uint64_t ll = p.out_labels[q * k + i];
+          int j = i - 1;
+          while (j >= 0 && p.out_dists[q * k + j] == dd && p.out_labels[q * k + j] > ll) {
+            p.out_dists[q * k + j + 1] = p.out_dists[q * k + j];
+            p.out_labels[q * k + j + 1] = p.out_labels[q * k + j];
+            j--;
+          }
+          p.out_dists[q * k + j + 1] = dd;
+          p.out_labels[q * k + j + 1] = ll;
+        }
+      }
+    }
+    if (lane == 0) {
+      p.out_found[q] = found;
+      if (p.out_stats) {
+        p.out_stats[q * 3 + 0] = hops;
+        p.out_stats[q * 3 + 1] = nbrs;
+        p.out_stats[q * 3 + 2] = evals;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// bitmap path: deletions and/or filter (literal two-structure walk with an exact visited set)
 // =================================================================================================
 __device__ __forceinline__ uint64_t pack_cand(float d, uint32_t id) { return ((uint64_t)__float_as_uint(d) << 32) | id; }
 __device__ __forceinline__ float cand_d(uint64_t c) { return __uint_as_float((uint32_t)(c >> 32)); }
@@ -1015,11 +1352,85 @@ int dispatch_code(annb_index *h, const SearchParams &p, bool general) {
   }
 }
 
+// ---- flagged walk launcher ---------------------------------------------------------------------------
+template <int EPL, int CR, int CB>
+int launch_flagged(annb_index *h, const SearchParams &p_in) {
+  SearchParams p = p_in;
+  const size_t table_bytes = (size_t)h->M * h->Ks * sizeof(float);
+  const size_t extra = (size_t)(32 * EPL + 33) * sizeof(uint2);
+  int max_warps = 32;
+  LaunchGeom geo = pick_geometry(h, table_bytes, extra, max_warps);
+  if (!geo.smem_table) return 1;  // not applicable: caller falls back to the bitmap walk
+  auto kern = hnsw_walk_flagged<EPL, CR, CB>;
+  int occ = 0, threads = 0, table_stride = (int)((table_bytes + 15) / 16 * 16);
+  for (;;) {
+    threads = geo.warps * 32;
+    if (geo.smem_bytes > 48 * 1024) ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes));
+    ANNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, geo.smem_bytes));
+    if (occ >= 1) break;
+    if (max_warps == 1) return 1;
+    max_warps = std::max(1, std::min(max_warps, geo.warps) / 2);
+    geo = pick_geometry(h, table_bytes, extra, max_warps);
+    if (!geo.smem_table) return 1;
+  }
+  occ = std::min(occ, geo.ctas_per_sm);
+  unsigned int *counter = p.work_counter;
+  if (!counter) {
+    int rc = annb_scratch(h, 4, 256, (void **)&counter);
+    if (rc) return rc;
+  }
+  ANNB_CUDA(cudaMemsetAsync(counter, 0, 8, h->stream));
+  p.work_counter = counter;
+  p.overflow_flag = reinterpret_cast<int32_t *>(counter + 1);
+  const int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
+  kern<<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, h->g.num_deleted > 0 ? 1 : 0, table_stride);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
+template <int EPL>
+int dispatch_flagged(annb_index *h, const SearchParams &p) {
+  const int cr = h->gd.code_row, cb = h->code_bytes;
+  if (cb == 1) {
+    switch (cr) {
+      case 4: return launch_flagged<EPL, 4, 1>(h, p);
+      case 8: return launch_flagged<EPL, 8, 1>(h, p);
+      case 16: return launch_flagged<EPL, 16, 1>(h, p);
+      case 32: return launch_flagged<EPL, 32, 1>(h, p);
+      default: return 1;
+    }
+  }
+  switch (cr) {
+    case 8: return launch_flagged<EPL, 8, 2>(h, p);
+    case 16: return launch_flagged<EPL, 16, 2>(h, p);
+    default: return 1;
+  }
+}
+
 }  // namespace
 
-int launch_search(annb_index *h, const SearchParams &p, bool general) {
+int launch_search(annb_index *h, const SearchParams &p, int mode) {
   if (p.B == 0) return ANNB_OK;
   if (p.B >= (int64_t)0xffffffffll) ANNB_FAIL(ANNB_ELIMIT, "at most 2^32-2 queries per call");
+  if (mode == 1 && h->gd.maxM0 <= 32 && h->gd.n < (1ll << 30)) {
+    // list capacity the flagged walk needs: every candidate down to the ef-th admitted one stays listed
+    const double s = std::min(1.0, std::max(1e-4, (double)p.selectivity));
+    // until the ef-th admitted node is found the list holds every evaluated node: about ef/s of them
+    // (binomial spread ~ sqrt(ef/s)); 1.3x + 48 leaves > 4 sigma of head-room at the usual sizes
+    const double need = (double)p.ef / s * 1.3 + 48.0;
+    int epl = 0;
+    for (int e : {2, 4, 8, 16})
+      if (epl == 0 && e * 32 >= need && e * 32 >= p.ef) epl = e;
+    if (h->opt_flagged_epl > 0 && h->opt_flagged_epl * 32 >= p.ef) epl = (int)h->opt_flagged_epl;
+    int rc = 1;
+    if (epl == 2) rc = dispatch_flagged<2>(h, p);
+    else if (epl == 4) rc = dispatch_flagged<4>(h, p);
+    else if (epl == 8) rc = dispatch_flagged<8>(h, p);
+    else if (epl == 16) rc = dispatch_flagged<16>(h, p);
+    if (rc != 1) return rc;  // launched (or failed for real); 1 = not applicable -> bitmap walk
+  }
+  const bool general = mode != 0;
   const int epl = (p.ef + 31) / 32;
   if (epl <= 2) return dispatch_code<2>(h, p, general);
   if (epl <= 4) return dispatch_code<4>(h, p, general);

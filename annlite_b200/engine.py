@@ -254,6 +254,12 @@ class Engine:
         L.check(self._lib.annb_launch_count(self._h, C.byref(n)))
         return n.value
 
+    @property
+    def fallback_count(self):
+        n = C.c_int64()
+        L.check(self._lib.annb_fallback_count(self._h, C.byref(n)))
+        return n.value
+
     def set_option(self, name, value):
         L.check(self._lib.annb_set_option(self._h, name.encode(), int(value)))
 

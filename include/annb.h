@@ -210,6 +210,8 @@ ANNB_API int annb_merge_topk(annb_index_t *h, const uint64_t *labels_gbk, const 
  * handle's stream) and launch counters since creation. */
 ANNB_API int annb_last_kernel_ms(annb_index_t *h, float *table_ms, float *search_ms, float *scan_ms);
 ANNB_API int annb_launch_count(annb_index_t *h, int64_t *out);
+/* number of filtered/deleted batches that outgrew the single-list walk and were re-run on the bitmap walk */
+ANNB_API int annb_fallback_count(annb_index_t *h, int64_t *out);
 ANNB_API int annb_set_option(annb_index_t *h, const char *name, int64_t value);
 
 #ifdef __cplusplus

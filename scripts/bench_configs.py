@@ -92,7 +92,7 @@ def c4(n=1_000_000):
     verdict = tie_aware_rows(l[:S], d[:S], ol, od)
     rel = np.abs(d[:S] - od)[l[:S] == ol] / np.maximum(np.abs(od[l[:S] == ol]), 1e-12)
     out = {'config': f'C4 {a.n} x 128d cosine, 50% filter bitmap ({len(allow)} ids), M=8, HNSW ef=64 k=10, {len(Q)} queries',
-           'index_build_s': t_build, 'gpu_filtered_qps_host_buffers': len(Q) / t_flt, 'gpu_filtered_kernel_ms': k_ms,
+           'index_build_s': t_build, 'gpu_filtered_qps_host_buffers': len(Q) / t_flt, 'gpu_filtered_kernel_ms': k_ms, 'flagged_walk_fallbacks': e.fallback_count,
            'gpu_unfiltered_qps_host_buffers': len(Q) / t_plain, 'all_results_pass_filter': bool(np.isin(l, allow).all()),
            'hops_per_query': float(st[:, 0].mean()), 'evals_per_query': float(st[:, 2].mean()),
            'parity_sample': S, 'rows_exact': verdict.count('exact'), 'rows_tie': verdict.count('tie'),

@@ -114,7 +114,7 @@ def _check(fx, l, d, ref_l, ref_d, allow_diff=0):
     return v
 
 
-@pytest.mark.parametrize('general', [0, 1])
+@pytest.mark.parametrize('general', [0, 1, 2])   # 0 fast walk, 1 flagged single-list walk, 2 bitmap walk
 def test_k3_knn_matches_reference(golden, general):
     e = engine(golden)
     e.set_option('force_general', general)
@@ -126,7 +126,7 @@ def test_k3_knn_matches_reference(golden, general):
     _, _, _, (hops, nbrs, evals) = O.hnsw_search(g, t, golden.k, golden.ef, with_counts=True)
     same = np.array([x == 'exact' for x in v])
     assert np.array_equal(st[same, 0], hops[same]) and np.array_equal(st[same, 1], nbrs[same])
-    if general:
+    if general == 2:   # exact visited set => the same number of distance evaluations as the reference
         assert np.array_equal(st[same, 2], evals[same])
 
 
@@ -141,16 +141,25 @@ def test_k3_fused_table_build(golden):
         _check(golden, l, d, golden.knn_labels, golden.knn_dists, 8 if golden.name == 'ties_k16' else 0)
 
 
-def test_k3_filtered_matches_reference(golden):
+@pytest.mark.parametrize('mode', ['auto', 'bitmap', 'tiny_list'])
+def test_k3_filtered_matches_reference(golden, mode):
     e = engine(golden)
+    if mode == 'bitmap':
+        e.set_option('force_general', 2)
+    if mode == 'tiny_list':          # a list too small for a 50 % filter: queries overflow and the batch is
+        e.set_option('flagged_epl', 2)                                 # re-run on the bitmap walk
     t = golden.query_tables_oracle()
     l, d = e.search(tables=t, k=golden.k, ef=golden.ef, filter_labels=golden.allow)
+    if mode == 'tiny_list' and golden.ef >= 50:   # 64 slots cannot hold ~2*ef candidates
+        assert e.fallback_count >= 1
     assert np.isin(l, golden.allow).all()
     _check(golden, l, d, golden.flt_labels, golden.flt_dists, 8 if golden.name == 'ties_k16' else 0)
 
 
-def test_k3_deleted_matches_reference(golden):
+@pytest.mark.parametrize('force', [0, 2])
+def test_k3_deleted_matches_reference(golden, force):
     e = engine(golden, deleted=True)
+    e.set_option('force_general', force)
     t = golden.query_tables_oracle()
     l, d = e.search(tables=t, k=golden.k, ef=golden.ef)
     assert not np.isin(l, golden.deleted).any()
