@@ -861,14 +861,33 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   // filter
   const uint32_t *dfilter = nullptr;
   if (filter_labels) {
-    const uint64_t *dfl;
-    ANNB_TRY(stage_in(h, filter_labels, filter_space, (size_t)std::max<int64_t>(n_filter, 1) * 8, S_FLT_LABELS, (const void **)&dfl));
-    if (h->max_label > (uint64_t)h->gd.n * 64 + (1ull << 30))
-      ANNB_FAIL(ANNB_ELIMIT, "labels up to %llu are too sparse for the device filter bitmap", (unsigned long long)h->max_label);
-    uint32_t *by_label, *by_id;
-    ANNB_TRY(annb_scratch(h, S_FLT_BY_LABEL, ((size_t)(h->max_label >> 5) + 1) * 4, (void **)&by_label));
+    uint32_t *by_id;
     ANNB_TRY(annb_scratch(h, S_FLT_BY_ID, ((size_t)(h->gd.n + 31) / 32 + 1) * 4, (void **)&by_id));
-    ANNB_TRY(launch_filter_bitmap(h, dfl, n_filter, by_label, by_id));
+    if (h->max_label > (uint64_t)h->gd.n * 64 + (1ull << 30)) {
+      // labels too sparse for a by-label bitmap on the device: resolve them through the host's
+      // label -> internal id map (the same map mark_deleted uses) and upload the by-id bitmap
+      std::vector<uint64_t> tmp;
+      const uint64_t *hl = filter_labels;
+      if (filter_space == ANNB_DEVICE) {
+        tmp.resize((size_t)n_filter);
+        ANNB_CUDA(cudaMemcpyAsync(tmp.data(), filter_labels, (size_t)n_filter * 8, cudaMemcpyDeviceToHost, h->stream));
+        ANNB_CUDA(cudaStreamSynchronize(h->stream));
+        hl = tmp.data();
+      }
+      std::vector<uint32_t> bm((size_t)(h->gd.n + 31) / 32 + 1, 0u);
+      for (int64_t i = 0; i < n_filter; i++) {
+        auto it = h->g.label_lookup.find(hl[i]);
+        if (it != h->g.label_lookup.end()) bm[it->second >> 5] |= 1u << (it->second & 31);
+      }
+      ANNB_CUDA(cudaMemcpyAsync(by_id, bm.data(), bm.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      ANNB_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+      const uint64_t *dfl;
+      ANNB_TRY(stage_in(h, filter_labels, filter_space, (size_t)std::max<int64_t>(n_filter, 1) * 8, S_FLT_LABELS, (const void **)&dfl));
+      uint32_t *by_label;
+      ANNB_TRY(annb_scratch(h, S_FLT_BY_LABEL, ((size_t)(h->max_label >> 5) + 1) * 4, (void **)&by_label));
+      ANNB_TRY(launch_filter_bitmap(h, dfl, n_filter, by_label, by_id));
+    }
     dfilter = by_id;
   }
   SearchParams p;

@@ -429,6 +429,25 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
 
     for (;;) {
       hops++;
+      // ---- nearest unexpanded entry of the current list; request its record right away: unless this
+      // hop finds something closer it is the next node, and its DRAM round trip then overlaps the
+      // whole hop (scoring + merge) ----
+      int pos2 = -1;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+        if (m && pos2 < 0) pos2 = e * 32 + __ffs(m) - 1;
+      }
+      uint2 e2 = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+      if (pos2 >= 0) e2 = sl[pos2];
+      uint32_t pred = LIST_EMPTY_VAL;
+      uint32_t link_n = EMPTY_LINK;
+      uint32_t cw_n[CW];
+      const uint8_t *code_ptr_n = nullptr;
+      if (pos2 >= 0) {
+        pred = e2.y & ID_MASK;
+        load_record(pred, link_n, cw_n, code_ptr_n);
+      }
       // ---- score the neighbour list (one lane = one neighbour, m sequential) ----
       const bool valid = link != EMPTY_LINK;
       float d = CUDART_INF_F;
@@ -445,16 +464,6 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
       const int nv = __popc(__ballot_sync(FULL_MASK, valid));
       nbrs += nv;
       evals += nv;
-
-      // ---- nearest unexpanded entry of the current list ----
-      int pos2 = -1;
-#pragma unroll
-      for (int e = 0; e < EPL; e++) {
-        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
-        if (m && pos2 < 0) pos2 = e * 32 + __ffs(m) - 1;
-      }
-      uint2 e2 = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
-      if (pos2 >= 0) e2 = sl[pos2];
 
       // ---- admission (:306) for the whole list at once: rank by binary search, drop re-encounters ----
       const bool take = valid && d < worst;
@@ -482,15 +491,12 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
         live = __ballot_sync(FULL_MASK, take && !dup);
       }
 
-      // ---- guess the next node and request its record now ----
+      // ---- a new candidate beats the entry whose record is already on its way: re-aim the prefetch ----
       const unsigned fm = __ballot_sync(FULL_MASK, ((live >> lane) & 1u) && d < __uint_as_float(e2.x));
-      uint32_t pred = LIST_EMPTY_VAL;
-      if (fm) pred = __shfl_sync(FULL_MASK, link, __ffs(fm) - 1);
-      else if (pos2 >= 0) pred = e2.y & ID_MASK;
-      uint32_t link_n = EMPTY_LINK;
-      uint32_t cw_n[CW];
-      const uint8_t *code_ptr_n = nullptr;
-      if (pred != LIST_EMPTY_VAL) load_record(pred, link_n, cw_n, code_ptr_n);
+      if (fm) {
+        pred = __shfl_sync(FULL_MASK, link, __ffs(fm) - 1);
+        load_record(pred, link_n, cw_n, code_ptr_n);
+      }
 
       // ---- merge the live candidates into the list ----
       int pos = pos2;
@@ -676,6 +682,21 @@ __global__ void hnsw_walk_flagged(const GraphDev g, const SearchParams p, const 
 
     for (;;) {
       hops++;
+      int pos2 = -1;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) {
+        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
+        if (m && pos2 < 0) pos2 = e * 32 + __ffs(m) - 1;
+      }
+      uint2 e2 = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
+      if (pos2 >= 0) e2 = sl[pos2];
+      uint32_t pred = LIST_EMPTY_VAL;
+      uint32_t link_n = EMPTY_LINK;
+      uint32_t cw_n[CW];
+      if (pos2 >= 0) {  // the likely next node: its record travels while this hop is scored and merged
+        pred = e2.y & ID_MASK30;
+        load_record(pred, link_n, cw_n);
+      }
       const bool valid = link != EMPTY_LINK;
       float d = CUDART_INF_F;
       bool pf = false;
@@ -689,15 +710,6 @@ __global__ void hnsw_walk_flagged(const GraphDev g, const SearchParams p, const 
       const int nv = __popc(__ballot_sync(FULL_MASK, valid));
       nbrs += nv;
       evals += nv;
-
-      int pos2 = -1;
-#pragma unroll
-      for (int e = 0; e < EPL; e++) {
-        const unsigned m = __ballot_sync(FULL_MASK, !(L.v[e] & EXPANDED_BIT));
-        if (m && pos2 < 0) pos2 = e * 32 + __ffs(m) - 1;
-      }
-      uint2 e2 = make_uint2(0x7f800000u, LIST_EMPTY_VAL);
-      if (pos2 >= 0) e2 = sl[pos2];
 
       // admission to candidate_set: top_candidates.size() < ef || lowerBound > dist (:306 / :413)
       const bool take = valid && (npass < ef || d < lb);
@@ -729,12 +741,10 @@ __global__ void hnsw_walk_flagged(const GraphDev g, const SearchParams p, const 
       }
 
       const unsigned fm = __ballot_sync(FULL_MASK, ((live >> lane) & 1u) && d < __uint_as_float(e2.x));
-      uint32_t pred = LIST_EMPTY_VAL;
-      if (fm) pred = __shfl_sync(FULL_MASK, link, __ffs(fm) - 1);
-      else if (pos2 >= 0) pred = e2.y & ID_MASK30;
-      uint32_t link_n = EMPTY_LINK;
-      uint32_t cw_n[CW];
-      if (pred != LIST_EMPTY_VAL) load_record(pred, link_n, cw_n);
+      if (fm) {
+        pred = __shfl_sync(FULL_MASK, link, __ffs(fm) - 1);
+        load_record(pred, link_n, cw_n);
+      }
 
       int pos = pos2;
       if (live) {

@@ -55,6 +55,7 @@ def parse():
     ap.add_argument('--no-cache', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=20000)
     ap.add_argument('--ref-sample', type=int, default=10000)
+    ap.add_argument('--chunks', type=int, default=0, help='host-buffer pipeline depth inside annb_search (0 = auto)')
     ap.add_argument('--pool', type=int, default=4, help='distinct query batches cycled through the steps')
     return ap.parse_args()
 
@@ -195,6 +196,8 @@ def run_ours(a):
         cb = obj[0]
     e = Engine(a.dim, a.m, a.ks, a.metric, device=local)
     e.set_codebook(cb)
+    if a.chunks:
+        e.set_option('chunks', a.chunks)
     os.makedirs(CACHE, exist_ok=True)
     t_build = 0.0
     if shard:

@@ -207,9 +207,8 @@ def hnsw_search(g: Graph, tables, k, ef, filter_labels=None, with_counts=False):
     bm = None
     if filter_labels is not None:
         fl = np.asarray(filter_labels, dtype=np.uint64)
-        maxlab = int(max(g.labels().max() if g.n else 0, fl.max() if fl.size else 0))
-        bm = np.zeros(maxlab // 8 + 1, dtype=np.uint8)
-        np.bitwise_or.at(bm, (fl >> np.uint64(3)).astype(np.int64), (1 << (fl & np.uint64(7))).astype(np.uint8))
+        member = np.isin(g.labels(), fl)          # membership is by label; the C side tests by internal id
+        bm = np.packbits(np.concatenate([member, np.zeros(8, dtype=bool)]), bitorder='little')
     lib().orc_hnsw_search(_p(g.level0), C.c_uint64(g.size_per_elem), C.c_uint64(g.offset_data),
                           C.c_uint64(g.label_offset), _p(g.links), _p(g.link_off), _p(g.levels),
                           C.c_uint64(g.size_links_per_elem), C.c_int64(g.n), C.c_int32(g.maxlevel),

@@ -198,7 +198,8 @@ static inline uint32_t g_link(const uint8_t *ll, unsigned j) { uint32_t v; memcp
 typedef struct { pq_t top, cand; uint32_t *visited; uint32_t tag; } ws_t;
 
 /* hnswalg.h:243-329 searchBaseLayerST<has_deletions, true>  (filter == NULL)
- * hnswalg.h:332-440 searchBaseLayerSTWithFilter             (filter != NULL: bit per *label*; the
+ * hnswalg.h:332-440 searchBaseLayerSTWithFilter             (filter != NULL: bit per internal id, set by
+ * the Python wrapper for every node whose *label* is in the caller's list; the
  * reference tests binary_fuse16_contain(label), an approximate set with ~2^-16 false positives;
  * the exact bitmap is what that filter approximates -- SURVEY.md section 2 row 6). */
 static void search_base(const graph_t *g, const float *table, uint32_t ep, size_t ef, int has_del,
@@ -206,7 +207,7 @@ static void search_base(const graph_t *g, const float *table, uint32_t ep, size_
   w->top.n = w->cand.n = 0;
   w->tag++;
   float lower;
-  int ep_ok = filter ? (int)((filter[g_label(g, ep) >> 3] >> (g_label(g, ep) & 7)) & 1) : (!has_del || !g_deleted(g, ep));
+  int ep_ok = filter ? (int)((filter[ep >> 3] >> (ep & 7)) & 1) : (!has_del || !g_deleted(g, ep));
   if (ep_ok) {
     float d = pq_lookup(table, g->M, g->Ks, g_code(g, ep), g->code_bytes);
     (*evals)++;
@@ -236,7 +237,7 @@ static void search_base(const graph_t *g, const float *table, uint32_t ep, size_
       if (w->top.n < ef || lower > d) {
         pq_push(&w->cand, -d, cid);
         int admit;
-        if (filter) { uint64_t l = g_label(g, cid); admit = (filter[l >> 3] >> (l & 7)) & 1; }   /* :423-426 */
+        if (filter) admit = (filter[cid >> 3] >> (cid & 7)) & 1;                                /* :423-426 */
         else admit = !has_del || !g_deleted(g, cid);                                            /* :314 */
         if (admit) pq_push(&w->top, d, cid);
         if (w->top.n > ef) pq_pop(&w->top);

@@ -1,0 +1,140 @@
+"""GPU: edge cases of the search path -- tiny / empty indexes, k vs ef vs n, huge sparse labels, empty and
+degenerate filters, incremental growth with device re-sync, argument errors."""
+import numpy as np
+import pytest
+
+import oracle as O
+from annlite_b200 import _lib as L
+from annlite_b200.engine import Engine
+from helpers import bits, tie_aware_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def small(n, D=16, M=4, Ks=16, seed=0, labels=None):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((max(n, Ks), D)).astype(np.float32)
+    ds = D // M
+    cb = np.stack([X[rng.choice(len(X), Ks, replace=False), m * ds:(m + 1) * ds] for m in range(M)]).astype(np.float32)
+    e = Engine(D, M, Ks, 'euclidean')
+    e.set_codebook(cb)
+    e.init_graph(max(n, 1) + 8, M=4, ef_construction=20)
+    lab = np.arange(n, dtype=np.uint64) if labels is None else labels
+    if n:
+        e.add_items(X[:n], lab, num_threads=1)
+    Q = rng.standard_normal((9, D)).astype(np.float32)
+    return e, cb, X[:n], Q, lab
+
+
+def oracle_same(e, cb, Q, k, ef, flt=None, M=4, Ks=16):
+    g = O.Graph.from_state(e.get_graph(), M, Ks)
+    t = O.adc_table(Q, cb)
+    ol, od, found = O.hnsw_search(g, t, k, ef, filter_labels=flt)
+    return ol, od, found
+
+
+def test_empty_index_raises_like_the_reference():
+    e, cb, X, Q, lab = small(0)
+    with pytest.raises(RuntimeError, match='Cannot return the results in a contigious 2D array'):
+        e.search(queries=Q, k=1, ef=10)
+    assert e.element_count == 0
+    l, d = e.search(queries=Q[:0], k=1, ef=10)      # zero queries is fine
+    assert l.shape == (0, 1)
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 33])
+def test_tiny_indexes(n):
+    e, cb, X, Q, lab = small(n)
+    k = min(n, 3)
+    l, d = e.search(queries=Q, k=k, ef=10)
+    ol, od, found = oracle_same(e, cb, Q, k, 10)
+    assert (found == k).all()
+    assert tie_aware_rows(l, d, ol, od).count('diff') == 0
+    if n < 4:
+        with pytest.raises(RuntimeError, match='Cannot return the results'):
+            e.search(queries=Q, k=n + 1, ef=10)      # fewer than k reachable results
+
+
+def test_k_larger_than_ef_uses_max():
+    e, cb, X, Q, lab = small(400)
+    l, d = e.search(queries=Q, k=40, ef=5)           # searchKnn uses max(ef, k)  (hnswalg.h:1279)
+    ol, od, _ = oracle_same(e, cb, Q, 40, 5)
+    assert tie_aware_rows(l, d, ol, od).count('diff') == 0
+    with pytest.raises(L.AnnbError) as ei:
+        e.search(queries=Q, k=10, ef=L.MAX_EF + 1)
+    assert ei.value.code == L.ELIMIT
+
+
+def test_huge_sparse_labels_and_filters():
+    rng = np.random.default_rng(3)
+    labels = np.unique(rng.integers(1, 2 ** 62, 600, dtype=np.uint64))[:500]
+    rng.shuffle(labels)
+    e, cb, X, Q, lab = small(500, labels=labels)
+    l, d = e.search(queries=Q, k=5, ef=32)
+    assert np.isin(l, labels).all()
+    ol, od, _ = oracle_same(e, cb, Q, 5, 32)
+    assert tie_aware_rows(l, d, ol, od).count('diff') == 0
+    allow = labels[::2]
+    l, d = e.search(queries=Q, k=5, ef=32, filter_labels=allow)   # host-side label resolution path
+    assert np.isin(l, allow).all()
+    ol, od, _ = oracle_same(e, cb, Q, 5, 32, flt=allow)
+    assert tie_aware_rows(l, d, ol, od).count('diff') == 0
+    # labels that are not in the index are ignored, as a fuse filter built from them would be
+    l2, d2 = e.search(queries=Q, k=5, ef=32, filter_labels=np.concatenate([allow, np.array([7, 9], dtype=np.uint64)]))
+    assert np.array_equal(l, l2)
+
+
+def test_degenerate_filters():
+    e, cb, X, Q, lab = small(300)
+    with pytest.raises(RuntimeError, match='Cannot return the results'):
+        e.search(queries=Q, k=3, ef=16, filter_labels=np.zeros(0, dtype=np.uint64))
+    one = lab[[17]]
+    ol, od, found = oracle_same(e, cb, Q, 1, 16, flt=one)
+    try:
+        l, d = e.search(queries=Q, k=1, ef=16, filter_labels=one)
+        assert (found == 1).all() and (l == 17).all()
+    except RuntimeError:
+        assert (found < 1).any()       # the reference's filtered walk can stop early too (no size==ef guard)
+
+
+def test_incremental_growth_resyncs_device_graph():
+    rng = np.random.default_rng(5)
+    D, M, Ks = 16, 4, 16
+    X = rng.standard_normal((600, D)).astype(np.float32)
+    cb = np.stack([X[rng.choice(600, Ks, replace=False), m * 4:(m + 1) * 4] for m in range(M)]).astype(np.float32)
+    e = Engine(D, M, Ks, 'euclidean')
+    e.set_codebook(cb)
+    e.init_graph(100, M=8, ef_construction=40)
+    Q = rng.standard_normal((16, D)).astype(np.float32)
+    done = 0
+    for step in (50, 50, 200, 300):
+        if done + step > 100 and e.graph_info()['max_elements'] < done + step:
+            e.resize_index(done + step)
+        e.add_items(X[done:done + step], np.arange(done, done + step, dtype=np.uint64), num_threads=1)
+        done += step
+        l, d = e.search(queries=Q, k=5, ef=32)
+        assert (l < done).all()
+        ol, od, _ = oracle_same(e, cb, Q, 5, 32)
+        assert tie_aware_rows(l, d, ol, od).count('diff') == 0
+    # the incremental single-threaded graph equals a one-shot single-threaded build
+    e2 = Engine(D, M, Ks, 'euclidean')
+    e2.set_codebook(cb)
+    e2.init_graph(600, M=8, ef_construction=40)
+    e2.add_items(X, np.arange(600, dtype=np.uint64), num_threads=1)
+    a, b = e.get_graph(), e2.get_graph()
+    assert np.array_equal(a['data_level0'], b['data_level0']) and np.array_equal(a['link_lists'], b['link_lists'])
+
+
+def test_argument_errors():
+    e, cb, X, Q, lab = small(50)
+    with pytest.raises(L.AnnbError):
+        e._lib.annb_search(e._h, None, None, 0, 1, 0, 1, 10, None, 0, 0, Q.ctypes.data, Q.ctypes.data, 0, None) and L.check(-1)
+    rc = e._lib.annb_search(e._h, None, None, 0, 1, 0, 1, 10, None, 0, 0, Q.ctypes.data, Q.ctypes.data, 0, None)
+    assert rc == L.EINVAL and b'exactly one of' in e._lib.annb_last_error()
+    with pytest.raises(RuntimeError, match='already indexed'):
+        e.add_items(X[:1], lab[:1])
+    e2 = Engine(16, 4, 16)
+    with pytest.raises(L.AnnbError, match='train the PQ'):
+        e2.adc_table(Q)
+    with pytest.raises(ValueError, match='Initialization Error'):
+        Engine(18, 4, 16)
