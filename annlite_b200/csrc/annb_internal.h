@@ -158,10 +158,18 @@ struct annb_index {
   size_t cap_rec0 = 0, cap_up = 0, cap_labels = 0, cap_deleted = 0;
 
   // scratch (grown on demand)
-  void *d_scratch[18] = {nullptr};
-  size_t scratch_cap[18] = {0};
-  void *h_pinned[4] = {nullptr};
-  size_t pinned_cap[4] = {0};
+  void *d_scratch[26] = {nullptr};
+  size_t scratch_cap[26] = {0};
+  void *h_pinned[6] = {nullptr};
+  size_t pinned_cap[6] = {0};
+  // asynchronous submit/wait lanes (annb_search_submit): lane i works on stream i with its own scratch
+  struct AsyncLane {
+    bool busy = false;
+    int64_t B = 0;
+    int k = 0;
+    int32_t *hfound = nullptr;
+  } lanes[2];
+  uint32_t next_ticket = 0;
 
   uint64_t max_label = 0;          // largest label in the graph (filter bitmap sizing)
   bool labels_identity = true;     // label[i] == i for all nodes

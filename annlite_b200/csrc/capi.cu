@@ -21,7 +21,8 @@ void annb_set_error(const char *fmt, ...) {
 
 enum {
   S_QUERIES = 0, S_TABLES, S_OUT_D, S_OUT_L, S_COUNTER, S_VISITED, S_TOUCHED, S_CAND,
-  S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I
+  S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I,
+  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS
 };
 
 int annb_scratch(annb_index *h, int slot, size_t bytes, void **out) {
@@ -29,6 +30,7 @@ int annb_scratch(annb_index *h, int slot, size_t bytes, void **out) {
   if (h->scratch_cap[slot] < bytes) {
     if (h->d_scratch[slot]) {
       ANNB_CUDA(cudaStreamSynchronize(h->stream));
+      if (h->stream2) ANNB_CUDA(cudaStreamSynchronize(h->stream2));
       ANNB_CUDA(cudaFree(h->d_scratch[slot]));
       h->d_scratch[slot] = nullptr;
       h->scratch_cap[slot] = 0;
@@ -52,6 +54,7 @@ int annb_pinned(annb_index *h, int slot, size_t bytes, void **out) {
   if (h->pinned_cap[slot] < bytes) {
     if (h->h_pinned[slot]) {
       ANNB_CUDA(cudaStreamSynchronize(h->stream));
+      if (h->stream2) ANNB_CUDA(cudaStreamSynchronize(h->stream2));
       ANNB_CUDA(cudaFreeHost(h->h_pinned[slot]));
       h->h_pinned[slot] = nullptr;
       h->pinned_cap[slot] = 0;
@@ -199,11 +202,14 @@ int annb_stream(annb_index_t *h, uint64_t *stream_out) {
   return ANNB_OK;
 }
 
+static int lane_wait(annb_index *h, int lane);
 int annb_sync(annb_index_t *h) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  int rc0 = lane_wait(h, 0), rc1 = lane_wait(h, 1);
   ANNB_CUDA(cudaStreamSynchronize(h->stream));
-  return ANNB_OK;
+  ANNB_CUDA(cudaStreamSynchronize(h->stream2));
+  return rc0 ? rc0 : rc1;
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------
@@ -929,6 +935,111 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
     if (hfound[b] < k)
       ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
   return ANNB_OK;
+}
+
+// ---- streaming submit / wait ---------------------------------------------------------------------
+static int lane_wait(annb_index *h, int lane) {
+  annb_index::AsyncLane &L = h->lanes[lane];
+  if (!L.busy) return ANNB_OK;
+  cudaStream_t st = lane ? h->stream2 : h->stream;
+  ANNB_CUDA(cudaStreamSynchronize(st));
+  L.busy = false;
+  for (int64_t b = 0; b < L.B; b++)
+    if (L.hfound[b] < L.k)
+      ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
+  return ANNB_OK;
+}
+
+int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k, int ef,
+                       uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (!queries || !labels_out || !dists_out || !ticket_out || B <= 0 || k <= 0 || ef <= 0) ANNB_FAIL(ANNB_EINVAL, "bad arguments");
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
+  if (h->g.num_deleted > 0 || h->opt_force_general)
+    ANNB_FAIL(ANNB_EINVAL, "annb_search_submit serves the plain search only (no deleted nodes / filters): use annb_search");
+  if (h->dev_dirty || h->deleted_dirty) {  // re-upload of the graph: nothing may be in flight
+    ANNB_TRY(lane_wait(h, 0));
+    ANNB_TRY(lane_wait(h, 1));
+    ANNB_TRY(sync_device_graph(h));
+  }
+  if (h->gd.n == 0) ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
+  const int ef_eff = std::max(ef, k);
+  if (ef_eff > ANNB_MAX_EF) ANNB_FAIL(ANNB_ELIMIT, "max(ef, k)=%d exceeds ANNB_MAX_EF=%d", ef_eff, ANNB_MAX_EF);
+  const int ticket = (int)(h->next_ticket++ & 0x3fffffff);
+  const int lane = ticket & 1;
+  ANNB_TRY(lane_wait(h, lane));  // a lane holds one batch at a time
+  const bool host_in = in_space != ANNB_DEVICE, host_out = out_space != ANNB_DEVICE;
+  const size_t TS = (size_t)h->M * h->Ks;
+  float *dq = nullptr, *dtab, *dd = dists_out;
+  uint64_t *dl = labels_out;
+  int32_t *dfound;
+  unsigned int *counters;
+  // all scratch first: a (re)allocation synchronises both lanes, which is only safe before enqueuing
+  if (host_in || normalize > 0) ANNB_TRY(annb_scratch(h, lane ? S_L1_QUERIES : S_QUERIES, (size_t)B * h->dim * sizeof(float), (void **)&dq));
+  ANNB_TRY(annb_scratch(h, lane ? S_L1_TABLES : S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
+  if (host_out) {
+    ANNB_TRY(annb_scratch(h, lane ? S_L1_OUT_L : S_OUT_L, (size_t)B * k * 8, (void **)&dl));
+    ANNB_TRY(annb_scratch(h, lane ? S_L1_OUT_D : S_OUT_D, (size_t)B * k * 4, (void **)&dd));
+  }
+  ANNB_TRY(annb_scratch(h, lane ? S_L1_FOUND : S_L0_FOUND, (size_t)B * 4, (void **)&dfound));
+  ANNB_TRY(annb_scratch(h, S_LANE_COUNTERS, 512, (void **)&counters));
+  int32_t *hfound;
+  ANNB_TRY(annb_pinned(h, 4 + lane, (size_t)B * 4, (void **)&hfound));
+
+  cudaStream_t saved = h->stream;
+  h->stream = lane ? h->stream2 : saved;
+  int rc = ANNB_OK;
+  const float *src = queries;
+  if (host_in || normalize > 0) {
+    if (cudaMemcpyAsync(dq, queries, (size_t)B * h->dim * sizeof(float), host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                        h->stream) != cudaSuccess)
+      rc = ANNB_ECUDA;
+    src = dq;
+  }
+  for (int r = 0; r < normalize && rc == ANNB_OK; r++) rc = launch_l2_normalize(h, dq, B, h->dim);
+  if (rc == ANNB_OK) rc = launch_adc_table(h, src, B, dtab);
+  if (rc == ANNB_OK) {
+    SearchParams p;
+    memset(&p, 0, sizeof(p));
+    p.tables = dtab;
+    p.B = B;
+    p.k = k;
+    p.ef = ef_eff;
+    p.out_labels = dl;
+    p.out_dists = dd;
+    p.out_found = dfound;
+    p.work_counter = counters + 64 * lane;
+    p.selectivity = 1.f;
+    rc = launch_search(h, p, 0);
+  }
+  if (rc == ANNB_OK) {
+    cudaMemcpyAsync(hfound, dfound, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (host_out) {
+      cudaMemcpyAsync(labels_out, dl, (size_t)B * k * 8, cudaMemcpyDeviceToHost, h->stream);
+      cudaMemcpyAsync(dists_out, dd, (size_t)B * k * 4, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (cudaGetLastError() != cudaSuccess) rc = ANNB_ECUDA;
+  }
+  h->stream = saved;
+  if (rc != ANNB_OK) {
+    if (rc == ANNB_ECUDA) annb_set_error("CUDA error while enqueuing a streamed search");
+    return rc;
+  }
+  h->lanes[lane].busy = true;
+  h->lanes[lane].B = B;
+  h->lanes[lane].k = k;
+  h->lanes[lane].hfound = hfound;
+  *ticket_out = ticket;
+  return ANNB_OK;
+}
+
+int annb_search_wait(annb_index_t *h, int ticket) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (ticket < 0) ANNB_FAIL(ANNB_EINVAL, "bad ticket");
+  return lane_wait(h, ticket & 1);
 }
 
 int annb_merge_topk(annb_index_t *h, const uint64_t *labels_gbk, const float *dists_gbk, int G, int64_t B, int k,

@@ -228,6 +228,27 @@ class Engine:
             return out_labels, out_dists, stats
         return out_labels, out_dists
 
+    def search_submit(self, queries, out_labels, out_dists, k=10, ef=50, normalize=0):
+        """Streaming form: enqueue one batch (host numpy or device torch buffers) and return a ticket; up
+        to two batches are in flight.  The buffers must stay alive and untouched until `search_wait`."""
+        q = self._as_f32(queries)
+        qp, qs, k0 = L.as_ptr(q)
+        lp, ls, k1 = L.as_ptr(out_labels)
+        dp, ds_, k2 = L.as_ptr(out_dists)
+        assert ls == ds_
+        t = C.c_int()
+        L.check(self._lib.annb_search_submit(self._h, qp, qs, q.shape[0], int(normalize), int(k), int(ef), lp, dp, ls,
+                                             C.byref(t)))
+        self._inflight = getattr(self, '_inflight', {})
+        self._inflight[t.value] = (k0, k1, k2)      # keep the buffers alive
+        return t.value
+
+    def search_wait(self, ticket):
+        try:
+            L.check(self._lib.annb_search_wait(self._h, int(ticket)))
+        finally:
+            getattr(self, '_inflight', {}).pop(ticket, None)
+
     def merge_topk(self, labels_gbk, dists_gbk, out_labels, out_dists):
         G, B, k = labels_gbk.shape
         L.check(self._lib.annb_merge_topk(self._h, labels_gbk.data_ptr(), dists_gbk.data_ptr(), G, B, k,

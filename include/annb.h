@@ -198,6 +198,16 @@ ANNB_API int annb_search(annb_index_t *h, const float *queries, const float *tab
                 int64_t n_filter, uint64_t *labels_out, float *dists_out, int out_space,
                 int64_t *stats_out);
 
+/* Streaming form of annb_search for serving loops (plain search only: no filter, no deleted nodes, no
+ * stats).  annb_search_submit enqueues upload (host inputs), K1, K3 and download (host outputs) of one batch
+ * on one of two internal lanes and returns a ticket at once; annb_search_wait blocks until that batch is
+ * complete and reports ANNB_EFEWRESULTS like annb_search.  Two batches can be in flight, so the copies of
+ * batch i+1 overlap the walk of batch i.  Buffers of a submitted batch belong to the library until its wait
+ * returns; a third submit first waits for the oldest ticket of its lane. */
+ANNB_API int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k,
+                       int ef, uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out);
+ANNB_API int annb_search_wait(annb_index_t *h, int ticket);
+
 /* ---- shard merge (CellContainer.ivf_search merge rule, annlite/container.py:130-138) ---------- */
 
 /* G per-shard result lists (G,B,k) (as all-gathered over NCCL) -> (B,k) global top-k by

@@ -134,3 +134,43 @@ def test_oracle_agrees_on_a_sample(big):
     assert same.mean() >= 0.99
     assert np.array_equal(bits(d[same]), bits(od[same]))
     assert np.array_equal(st[same, 0], hops[same]) and np.array_equal(st[same, 1], nbrs[same])
+
+
+def test_streamed_submit_wait_matches_blocking_calls(big):
+    torch = pytest.importorskip('torch')
+    e = big['e']
+    Q = big['Q']
+    ref = [e.search(queries=Q[i * 512:(i + 1) * 512], k=10, ef=64) for i in range(6)]
+    # host buffers, two batches in flight
+    outs = [(np.empty((512, 10), np.uint64), np.empty((512, 10), np.float32)) for _ in range(6)]
+    tickets = []
+    for i in range(6):
+        if len(tickets) == 2:
+            e.search_wait(tickets.pop(0))
+        tickets.append(e.search_submit(Q[i * 512:(i + 1) * 512], outs[i][0], outs[i][1], k=10, ef=64))
+    while tickets:
+        e.search_wait(tickets.pop(0))
+    for (l, d), (rl, rd) in zip(outs, ref):
+        assert np.array_equal(l, rl) and np.array_equal(bits(d), bits(rd))
+    # device buffers
+    qd = torch.from_numpy(Q).cuda()
+    dl = [torch.empty((512, 10), dtype=torch.int64, device='cuda') for _ in range(6)]
+    dd = [torch.empty((512, 10), dtype=torch.float32, device='cuda') for _ in range(6)]
+    t = [e.search_submit(qd[i * 512:(i + 1) * 512], dl[i], dd[i], k=10, ef=64) for i in range(6)]   # a 3rd submit waits for its lane
+    for x in t:
+        e.search_wait(x)
+    e.sync()
+    for i, (rl, rd) in enumerate(ref):
+        assert np.array_equal(dl[i].cpu().numpy().view(np.uint64), rl) and np.array_equal(bits(dd[i].cpu().numpy()), bits(rd))
+    # a blocking call in between streamed ones is fine
+    t0 = e.search_submit(Q[:512], outs[0][0], outs[0][1], k=10, ef=64)
+    l, d = e.search(queries=Q[512:1024], k=10, ef=64)
+    e.search_wait(t0)
+    assert np.array_equal(l, ref[1][0]) and np.array_equal(outs[0][0], ref[0][0])
+    # too few results surface at wait()
+    with pytest.raises(RuntimeError, match='plain search only'):
+        e.set_option('force_general', 1)
+        try:
+            e.search_submit(Q[:8], outs[0][0][:8], outs[0][1][:8], k=10, ef=64)
+        finally:
+            e.set_option('force_general', 0)
