@@ -120,6 +120,21 @@ class HnswIndex:
                 dists.sqrt_()
         return dists, ids
 
+    def search_batch_submit(self, queries, limit: int = 10):
+        """Streamed batched search for serving loops (no filter): returns a ticket at once, two batches can
+        be in flight so the transfers of one overlap the graph walk of the other."""
+        self._ensure_backend()
+        if isinstance(queries, np.ndarray) or not hasattr(queries, 'data_ptr'):
+            queries = self._prep(queries)
+        self._index.set_ef(max(self.ef_search, limit))
+        return self._index.knn_query_submit(queries, k=limit, normalize=self._normalize_rounds)
+
+    def search_batch_wait(self, ticket):
+        ids, dists = self._index.knn_query_wait(ticket)
+        if self.metric == Metric.EUCLIDEAN:
+            dists = np.sqrt(dists) if isinstance(dists, np.ndarray) else dists.sqrt_()
+        return dists, ids
+
     def delete(self, ids: List[int]):
         for i in ids:
             self._index.mark_deleted(i)

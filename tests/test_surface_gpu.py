@@ -138,6 +138,12 @@ def test_hnsw_index_matches_reference_semantics(golden, tmp_path):
     d1, i1 = h.search_batch(golden.Q, limit=golden.k)
     d2, i2 = h2.search_batch(golden.Q, limit=golden.k)
     assert np.array_equal(i1, i2)
+    # streamed form returns the same thing
+    t1 = h.search_batch_submit(golden.Q[:32], limit=golden.k)
+    t2 = h.search_batch_submit(golden.Q[32:], limit=golden.k)
+    ds1, is1 = h.search_batch_wait(t1)
+    ds2, is2 = h.search_batch_wait(t2)
+    assert np.array_equal(np.vstack([is1, is2]), i1) and np.allclose(np.vstack([ds1, ds2]), d1, rtol=1e-6)
     h.delete([int(golden.labels[0])])
     with pytest.raises(RuntimeError, match='update operation is not allowed'):
         h.update_with_ids(golden.X[:1], [0])
