@@ -501,6 +501,8 @@ int annb_add_items(annb_index_t *h, const float *vectors, const void *codes, con
   if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
   if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph first");
   if (n == 0) return ANNB_OK;
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));   // insertion reuses search scratch: let streamed searches finish
+  ANNB_CUDA(cudaStreamSynchronize(h->stream2));
   const size_t crow = (size_t)h->M * h->code_bytes;
   std::vector<uint8_t> own_codes;
   const uint8_t *hc = (const uint8_t *)codes;
@@ -654,10 +656,12 @@ static int upload_deleted(annb_index *h) {
 int sync_device_graph(annb_index *h) {
   HostGraph &g = h->g;
   if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
-  if (!h->dev_dirty) {
-    if (h->deleted_dirty) return upload_deleted(h);
-    return ANNB_OK;
-  }
+  if (!h->dev_dirty && !h->deleted_dirty) return ANNB_OK;
+  // device buffers are about to be rewritten / reallocated: nothing may still be walking them
+  // (streamed searches of annb_search_submit run on both lanes)
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->stream2) ANNB_CUDA(cudaStreamSynchronize(h->stream2));
+  if (!h->dev_dirty) return upload_deleted(h);
   const int64_t n = g.count.load();
   GraphDev &d = h->gd;
   memset(&d, 0, sizeof(d));
