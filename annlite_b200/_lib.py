@@ -55,6 +55,7 @@ PROTOTYPES = {
     'annb_get_labels': (_int, [_vp, _vp, _i64]),
     'annb_get_codes': (_int, [_vp, _vp, _i64, _vp]),
     'annb_search': (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _int, _vp, _int, _i64, _vp, _vp, _int, _vp]),
+    'annb_scan_subset': (_int, [_vp, _vp, _int, _i64, _int, _int, _vp, _i64, _vp, _vp]),
     'annb_search_submit': (_int, [_vp, _vp, _int, _i64, _int, _int, _int, _vp, _vp, _int, C.POINTER(_int)]),
     'annb_search_wait': (_int, [_vp, _int]),
     'annb_merge_topk': (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),

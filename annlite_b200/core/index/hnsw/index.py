@@ -22,7 +22,8 @@ class HnswIndex:
     def __init__(self, dim: int, dtype=np.float32, metric: Metric = Metric.COSINE, ef_construction: int = 200,
                  ef_search: int = 50, max_connection: int = 16, pq_codec=None,
                  index_file: Optional[Union[str, Path]] = None, initial_size: Optional[int] = None,
-                 expand_step_size: int = 10240, expand_mode: ExpandMode = ExpandMode.STEP, device: int = 0, **kwargs):
+                 expand_step_size: int = 10240, expand_mode: ExpandMode = ExpandMode.STEP, device: int = 0,
+                 bruteforce_filter_below: Optional[int] = None, **kwargs):
         assert expand_step_size > 0
         if isinstance(metric, str):
             metric = Metric.from_string(metric)
@@ -34,6 +35,9 @@ class HnswIndex:
         self.pq_codec = pq_codec
         self.index_file = index_file
         self.device = device
+        # opt-in: filters that admit at most this many ids are answered by an exact ADC scan over those ids
+        # instead of the filtered graph walk (the reference's own TODO, hnsw/index.py:152); None = reference behaviour
+        self.bruteforce_filter_below = bruteforce_filter_below
         if pq_codec is None:
             raise NotImplementedError('annlite_b200.HnswIndex is the PQ-encoded HNSW backend; pass a PQCodec '
                                       '(the float HNSW path is out of scope, SURVEY.md section 2 row 8)')
@@ -111,6 +115,10 @@ class HnswIndex:
         self._index.set_ef(max(self.ef_search, limit))
         if indices is not None and len(indices) < limit:
             limit = len(indices)
+        if (indices is not None and self.bruteforce_filter_below is not None
+                and len(indices) <= self.bruteforce_filter_below and out_ids is None):
+            ids, dists = self._index._e.scan_subset(queries, indices, k=limit, normalize=self._normalize_rounds)
+            return (np.sqrt(dists) if self.metric == Metric.EUCLIDEAN else dists), ids
         ids, dists = self._index.knn_query_vectors(queries, k=limit, normalize=self._normalize_rounds,
                                                    filters=indices, out_labels=out_ids, out_dists=out_dists)
         if self.metric == Metric.EUCLIDEAN:

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <limits>
 #include <cstdio>
 #include <cstring>
 
@@ -938,6 +939,72 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   for (int64_t b = 0; b < B; b++)
     if (hfound[b] < k)
       ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
+  return ANNB_OK;
+}
+
+int annb_scan_subset(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k,
+                     const uint64_t *subset_labels, int64_t n_subset, uint64_t *labels_out, float *dists_out) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (!queries || !labels_out || !dists_out || B < 0 || k <= 0 || n_subset < 0 || (n_subset > 0 && !subset_labels))
+    ANNB_FAIL(ANNB_EINVAL, "bad arguments");
+  if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  if (B == 0) return ANNB_OK;
+  HostGraph &g = h->g;
+  const size_t crow = g.code_row_bytes;
+  std::vector<uint8_t> codes;
+  std::vector<uint64_t> labs;
+  codes.reserve((size_t)n_subset * crow);
+  labs.reserve((size_t)n_subset);
+  for (int64_t i = 0; i < n_subset; i++) {
+    auto it = g.label_lookup.find(subset_labels[i]);
+    if (it == g.label_lookup.end() || g.deleted(it->second)) continue;
+    const uint8_t *c = g.code(it->second);
+    codes.insert(codes.end(), c, c + crow);
+    labs.push_back(subset_labels[i]);
+  }
+  const int64_t n = (int64_t)labs.size();
+  // the scan works on the handle's flat code matrix: keep the caller's one (annb_set_codes) intact
+  uint8_t *saved_codes = h->d_codes;
+  const int64_t saved_n = h->n_codes;
+  h->d_codes = nullptr;
+  h->n_codes = 0;
+  int rc = ANNB_OK;
+  std::vector<int64_t> ids((size_t)B * k);
+  if (n > 0) {
+    cudaError_t ce = cudaMalloc(&h->d_codes, (size_t)n * crow + 16);
+    if (ce != cudaSuccess) rc = ANNB_ENOMEM;
+    if (rc == ANNB_OK && cudaMemcpyAsync(h->d_codes, codes.data(), (size_t)n * crow, cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+      rc = ANNB_ECUDA;
+    h->n_codes = n;
+    float *t = nullptr, *dd = nullptr;
+    int64_t *dids = nullptr;
+    if (rc == ANNB_OK) rc = annb_scratch(h, S_TABLES, (size_t)B * h->M * h->Ks * sizeof(float), (void **)&t);
+    if (rc == ANNB_OK) rc = annb_scratch(h, S_OUT_L, (size_t)B * k * sizeof(int64_t), (void **)&dids);
+    if (rc == ANNB_OK) rc = annb_scratch(h, S_OUT_D, (size_t)B * k * sizeof(float), (void **)&dd);
+    if (rc == ANNB_OK) rc = build_tables(h, queries, in_space, B, normalize, t);
+    if (rc == ANNB_OK) rc = launch_scan_topk(h, t, B, k, dids, dd);
+    if (rc == ANNB_OK) {
+      cudaMemcpyAsync(ids.data(), dids, (size_t)B * k * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+      cudaMemcpyAsync(dists_out, dd, (size_t)B * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+      if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = ANNB_ECUDA;
+    }
+    if (h->d_codes) cudaFree(h->d_codes);
+  }
+  h->d_codes = saved_codes;
+  h->n_codes = saved_n;
+  if (rc == ANNB_ECUDA) annb_set_error("CUDA error in annb_scan_subset: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == ANNB_ENOMEM) annb_set_error("cudaMalloc failed in annb_scan_subset");
+  if (rc != ANNB_OK) return rc;
+  for (int64_t i = 0; i < B * k; i++) {
+    if (n > 0 && ids[i] >= 0) {
+      labels_out[i] = labs[(size_t)ids[i]];
+    } else {
+      labels_out[i] = UINT64_MAX;
+      dists_out[i] = std::numeric_limits<float>::infinity();
+    }
+  }
+  if (n < k) ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
   return ANNB_OK;
 }
 

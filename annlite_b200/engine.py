@@ -228,6 +228,19 @@ class Engine:
             return out_labels, out_dists, stats
         return out_labels, out_dists
 
+    def scan_subset(self, queries, subset_labels, k=10, normalize=0):
+        """Exact ADC over the indexed nodes whose labels are in `subset_labels` (brute-force route for very
+        selective filters).  Returns (labels uint64 (B,k), dists fp32 (B,k))."""
+        q = self._as_f32(queries)
+        sub = np.ascontiguousarray(subset_labels, dtype=np.uint64)
+        B = q.shape[0]
+        labels = np.empty((B, k), dtype=np.uint64)
+        dists = np.empty((B, k), dtype=np.float32)
+        qp, qs, _k = L.as_ptr(q)
+        L.check(self._lib.annb_scan_subset(self._h, qp, qs, B, int(normalize), int(k), sub.ctypes.data if sub.size else None,
+                                           sub.shape[0], labels.ctypes.data, dists.ctypes.data))
+        return labels, dists
+
     def search_submit(self, queries, out_labels, out_dists, k=10, ef=50, normalize=0):
         """Streaming form: enqueue one batch (host numpy or device torch buffers) and return a ticket; up
         to two batches are in flight.  The buffers must stay alive and untouched until `search_wait`."""

@@ -198,6 +198,16 @@ ANNB_API int annb_search(annb_index_t *h, const float *queries, const float *tab
                 int64_t n_filter, uint64_t *labels_out, float *dists_out, int out_space,
                 int64_t *stats_out);
 
+/* Exhaustive ADC over a label subset of the INDEXED nodes (the brute-force route for
+ * very selective filters that HnswIndex.search leaves as a TODO, annlite/core/index/hnsw/index.py:152): the
+ * codes of the nodes whose labels are listed are gathered from the graph, scanned with K2 for every query and
+ * the k best returned as (labels, dists), ascending (dist, label order of the subset list).  Unknown and
+ * deleted labels are skipped; fewer than k candidates -> missing slots = UINT64_MAX / +inf and
+ * ANNB_EFEWRESULTS.  Opt-in from the Python side (it changes WHICH results come back compared with the
+ * reference's filtered graph walk: these are exact over the subset). */
+ANNB_API int annb_scan_subset(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k,
+                     const uint64_t *subset_labels, int64_t n_subset, uint64_t *labels_out, float *dists_out);
+
 /* Streaming form of annb_search for serving loops (plain search only: no filter, no deleted nodes, no
  * stats).  annb_search_submit enqueues upload (host inputs), K1, K3 and download (host outputs) of one batch
  * on one of two internal lanes and returns a ticket at once; annb_search_wait blocks until that batch is

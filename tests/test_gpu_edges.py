@@ -138,3 +138,57 @@ def test_argument_errors():
         e2.adc_table(Q)
     with pytest.raises(ValueError, match='Initialization Error'):
         Engine(18, 4, 16)
+
+
+def test_bruteforce_subset_scan_is_exact_over_the_subset():
+    """exact ADC over a small admissible id set (opt-in route for very selective filters)."""
+    e, cb, X, Q, lab = small(800, seed=21, labels=np.arange(800, dtype=np.uint64) * 5 + 2)
+    sub = lab[::37]                                      # 22 admissible labels
+    l, d = e.scan_subset(Q, sub, k=5)
+    g = O.Graph.from_state(e.get_graph(), 4, 16)
+    codes, glab = g.codes(), g.labels()
+    pos = {int(v): i for i, v in enumerate(glab)}
+    t = O.adc_table(Q, cb)
+    for b in range(len(Q)):
+        dd = O.scan(t[b], codes[[pos[int(x)] for x in sub]])
+        order = np.lexsort((np.arange(len(sub)), dd))[:5]
+        assert np.array_equal(l[b], sub[order]) and np.array_equal(bits(d[b]), bits(dd[order]))
+    # unknown labels are skipped, too few candidates raise like the walk does
+    l2, d2 = e.scan_subset(Q, np.concatenate([sub, np.array([1, 3], dtype=np.uint64)]), k=5)
+    assert np.array_equal(l, l2)
+    with pytest.raises(RuntimeError, match='Cannot return the results'):
+        e.scan_subset(Q, sub[:3], k=5)
+    # the flat code matrix of the handle (annb_set_codes) is left alone
+    e.set_codes(codes)
+    before = e.scan_topk(queries=Q, k=3)[0]
+    e.scan_subset(Q, sub, k=5)
+    assert np.array_equal(before, e.scan_topk(queries=Q, k=3)[0])
+
+
+def test_hnsw_index_opt_in_bruteforce_for_selective_filters():
+    from annlite_b200 import HnswIndex, Metric, PQCodec
+    rng = np.random.default_rng(31)
+    N, D = 3000, 16
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    codec = PQCodec(D, n_subvectors=4, n_clusters=16, metric=Metric.EUCLIDEAN)
+    codec.set_codebook(np.stack([X[rng.choice(N, 16, replace=False), m * 4:(m + 1) * 4] for m in range(4)]))
+    ref = HnswIndex(D, metric=Metric.EUCLIDEAN, pq_codec=codec, ef_search=32, initial_size=N)
+    bf = HnswIndex(D, metric=Metric.EUCLIDEAN, pq_codec=codec, ef_search=32, initial_size=N, bruteforce_filter_below=64)
+    for h in (ref, bf):
+        h.add_with_ids(X, list(range(N)), num_threads=1)
+    q = rng.standard_normal(D).astype(np.float32)
+    few = np.sort(rng.choice(N, 12, replace=False)).astype(np.uint64)
+    d, i = bf.search(q, limit=5, indices=few)                    # exact over the 12 admissible ids
+    assert np.isin(i, few).all() and (np.diff(d) >= 0).all()
+    codes = codec.encode(X[few.astype(np.int64)])
+    exact = np.sqrt(O.scan(O.adc_table(q[None], codec.codebooks)[0], codes))
+    assert np.allclose(np.sort(exact)[:5], d, rtol=1e-6)
+    try:                                                         # the reference-shaped walk may find fewer / others
+        d2, i2 = ref.search(q, limit=5, indices=few)
+        assert np.isin(i2, few).all() and d2[0] >= d[0] - 1e-6
+    except RuntimeError as ex:
+        assert 'Cannot return the results' in str(ex)
+    many = np.arange(0, N, 2, dtype=np.uint64)                   # above the threshold: both take the graph walk
+    da, ia = bf.search(q, limit=5, indices=many)
+    db, ib = ref.search(q, limit=5, indices=many)
+    assert np.array_equal(ia, ib)
