@@ -39,7 +39,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--n', type=int, default=1_000_000)
+    ap.add_argument('--n', '--base-n', dest='n', type=int, default=1_000_000)   # use --base-n under torchrun (its parser treats --n as ambiguous)
     ap.add_argument('--dim', type=int, default=128)
     ap.add_argument('--m', type=int, default=8)
     ap.add_argument('--ks', type=int, default=256)
@@ -404,7 +404,7 @@ def run_ours(a):
         else:
             rec_adc = rec_l2 = None
         # CPU baseline: C oracle port over the same graph, all host threads, bounded sample
-        cpu = cpu_port_baseline(a, e, Qh, cb, ncores) if not shard else None
+        cpu = cpu_port_baseline(a, e, Qh, cb, ncores) if world == 1 else None   # reported at N=1 only
         result = {
             'metric': 'queries/sec (PQ-HNSW search, 1M x 128d, M=8, ef=64, k=10)', 'value': round(value, 1),
             'unit': 'queries/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
