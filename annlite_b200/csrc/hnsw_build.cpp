@@ -18,6 +18,7 @@
 #include <queue>
 #include <random>
 #include <thread>
+#include <unordered_set>
 
 #include "annb_internal.h"
 
@@ -353,7 +354,7 @@ struct Worker {
   }
 
   // mutuallyConnectNewElement(point, cur, top_candidates, level, isUpdate=false): hnswalg.h:502-619
-  int connect(uint32_t cur, FarHeap &top, int level, uint32_t *next_ep) {
+  int connect(uint32_t cur, FarHeap &top, int level, uint32_t *next_ep, bool is_update = false) {
     const size_t Mcurmax = level ? (size_t)g.maxM : (size_t)g.maxM0;
     select_neighbors(top, (size_t)g.M);
     if (top.size() > (size_t)g.M) ANNB_FAIL(ANNB_EINVAL, "Should be not be more than M_ candidates returned by the heuristic");
@@ -366,11 +367,11 @@ struct Worker {
     *next_ep = sel.back();
     {
       uint8_t *ll = g.list_at(cur, level);
-      if (list_count(ll)) ANNB_FAIL(ANNB_EINVAL, "The newly inserted element should have blank link list");
+      if (list_count(ll) && !is_update) ANNB_FAIL(ANNB_EINVAL, "The newly inserted element should have blank link list");
       set_list_count(ll, (unsigned)sel.size());
       uint32_t *data = list_links(ll);
       for (size_t i = 0; i < sel.size(); i++) {
-        if (data[i]) ANNB_FAIL(ANNB_EINVAL, "Possible memory corruption");
+        if (data[i] && !is_update) ANNB_FAIL(ANNB_EINVAL, "Possible memory corruption");
         if (level > g.levels[sel[i]]) ANNB_FAIL(ANNB_EINVAL, "Trying to make a link on a non-existent level");
         data[i] = sel[i];
       }
@@ -384,6 +385,15 @@ struct Worker {
       if (other == cur) ANNB_FAIL(ANNB_EINVAL, "Trying to connect an element to itself");
       if (level > g.levels[other]) ANNB_FAIL(ANNB_EINVAL, "Trying to make a link on a non-existent level");
       uint32_t *data = list_links(ll);
+      if (is_update) {  // already linked back: leave the neighbour's list alone (:563-574)
+        bool present = false;
+        for (size_t j = 0; j < sz; j++)
+          if (data[j] == cur) {
+            present = true;
+            break;
+          }
+        if (present) continue;
+      }
       if (sz < Mcurmax) {
         data[sz] = cur;
         set_list_count(ll, (unsigned)sz + 1);
@@ -405,6 +415,108 @@ struct Worker {
     return ANNB_OK;
   }
 
+  std::vector<uint32_t> connections(uint32_t id, int level) {  // getConnectionsWithLock: hnswalg.h:1098-1106
+    SpinGuard lk(S.node_locks, id, S.threaded);
+    uint8_t *ll = g.list_at(id, level);
+    const unsigned n = list_count(ll);
+    const uint32_t *d = list_links(ll);
+    return std::vector<uint32_t>(d, d + n);
+  }
+
+  // repairConnectionsForUpdate: hnswalg.h:1036-1096
+  int repair(uint32_t ep, uint32_t id, int elem_level, int max_level) {
+    uint32_t cur_obj = ep;
+    if (elem_level < max_level) {
+      float curdist = dist_to_new(cur_obj);
+      for (int level = max_level; level > elem_level; level--) {
+        bool changed = true;
+        while (changed) {
+          changed = false;
+          SpinGuard lk(S.node_locks, cur_obj, S.threaded);
+          uint8_t *ll = g.list_at(cur_obj, level);
+          const unsigned size = list_count(ll);
+          const uint32_t *nb = list_links(ll);
+          for (unsigned i = 0; i < size; i++) {
+            const uint32_t c = nb[i];
+            const float d = dist_to_new(c);
+            if (d < curdist) {
+              curdist = d;
+              cur_obj = c;
+              changed = true;
+            }
+          }
+        }
+      }
+    }
+    if (elem_level > max_level) ANNB_FAIL(ANNB_EINVAL, "Level of item to be updated cannot be bigger than max level");
+    for (int level = elem_level; level >= 0; level--) {
+      FarHeap top = search_layer(cur_obj, level);
+      FarHeap filtered;
+      while (!top.empty()) {
+        if (top.top().second != id) filtered.push(top.top());
+        top.pop();
+      }
+      if (!filtered.empty()) {
+        if (g.deleted(ep)) {
+          filtered.emplace(dist_to_new(ep), ep);
+          if (filtered.size() > (size_t)g.ef_construction) filtered.pop();
+        }
+        int rc = connect(id, filtered, level, &cur_obj, true);
+        if (rc) return rc;
+      }
+    }
+    return ANNB_OK;
+  }
+
+  // updatePoint(point, internalId, updateNeighborProbability = 1.0): hnswalg.h:958-1034.  Re-adding an
+  // existing label (AnnLite.update -> add_with_ids, annlite/container.py:343-347) lands here.  With
+  // probability 1.0 the reference's update_probability_generator_ draws never skip a neighbour, so the
+  // generator is not modelled.  std::unordered_set reproduces the reference's iteration order.
+  int update(const uint8_t *code, uint32_t id) {
+    memcpy(g.rec0(id) + g.offset_data, code, g.code_row_bytes);
+    const int max_level_copy = g.maxlevel;
+    const uint32_t ep_copy = g.enterpoint;
+    if (ep_copy == id && g.count.load() == 1) return ANNB_OK;
+    const int elem_level = g.levels[id];
+    for (int layer = 0; layer <= elem_level; layer++) {
+      std::unordered_set<uint32_t> s_cand, s_neigh;
+      std::vector<uint32_t> one_hop = connections(id, layer);
+      if (one_hop.empty()) continue;
+      s_cand.insert(id);
+      for (uint32_t h1 : one_hop) {
+        s_cand.insert(h1);
+        s_neigh.insert(h1);
+        for (uint32_t h2 : connections(h1, layer)) s_cand.insert(h2);
+      }
+      for (uint32_t neigh : s_neigh) {
+        FarHeap cands;
+        const size_t size = s_cand.find(neigh) == s_cand.end() ? s_cand.size() : s_cand.size() - 1;
+        const size_t keep = std::min((size_t)g.ef_construction, size);
+        for (uint32_t c : s_cand) {
+          if (c == neigh) continue;
+          const float d = dist_to_new(c);  // PQLookup ignores its first argument
+          if (cands.size() < keep) {
+            cands.emplace(d, c);
+          } else if (d < cands.top().first) {
+            cands.pop();
+            cands.emplace(d, c);
+          }
+        }
+        select_neighbors(cands, layer == 0 ? (size_t)g.maxM0 : (size_t)g.maxM);
+        SpinGuard lk(S.node_locks, neigh, S.threaded);
+        uint8_t *ll = g.list_at(neigh, layer);
+        const size_t n = cands.size();
+        set_list_count(ll, (unsigned)n);
+        uint32_t *data = list_links(ll);
+        for (size_t i = 0; i < n; i++) {
+          data[i] = cands.top().second;
+          cands.pop();
+        }
+      }
+    }
+    return repair(ep_copy, id, elem_level, max_level_copy);
+  }
+
   int random_level() {  // getRandomLevel: hnswalg.h:151-155
     std::uniform_real_distribution<double> distribution(0.0, 1.0);
     double r;
@@ -417,16 +529,23 @@ struct Worker {
     return (int)r;
   }
 
-  // addPoint(point, label, level=-1): hnswalg.h:1108-1235 (new labels only)
+  // addPoint(point, label, level=-1): hnswalg.h:1108-1235
   int insert(const float *table, const uint8_t *code, uint64_t label) {
     T = table;
     uint32_t cur;
     {
       std::unique_lock<std::mutex> lk(S.count_guard, std::defer_lock);
       if (S.threaded) lk.lock();
-      if (g.label_lookup.find(label) != g.label_lookup.end())
-        ANNB_FAIL(ANNB_EINVAL, "label %llu already indexed: updating stored points is not supported by this backend",
-                  (unsigned long long)label);
+      auto found = g.label_lookup.find(label);
+      if (found != g.label_lookup.end()) {  // existing label: update in place (:1119-1131)
+        const uint32_t existing = found->second;
+        if (S.threaded) lk.unlock();
+        if (g.deleted(existing)) {
+          g.rec0(existing)[2] &= (uint8_t)~1;
+          g.num_deleted--;
+        }
+        return update(code, existing);
+      }
       if (g.count.load() >= g.max_elements) ANNB_FAIL(ANNB_ECAPACITY, "The number of elements exceeds the specified limit");
       cur = (uint32_t)g.count.load();
       g.count.store(cur + 1);
@@ -506,8 +625,15 @@ int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels
                      const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows) {
   HostGraph &g = h->g;
   if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph / annb_load_index first");
-  if (g.count.load() + n > g.max_elements) ANNB_FAIL(ANNB_ECAPACITY, "The number of elements exceeds the specified limit");
+  int64_t fresh = 0;
+  {
+    std::unordered_set<uint64_t> seen_in_batch;
+    for (int64_t i = 0; i < n; i++)
+      if (g.label_lookup.find(labels[i]) == g.label_lookup.end() && seen_in_batch.insert(labels[i]).second) fresh++;
+  }
+  if (g.count.load() + fresh > g.max_elements) ANNB_FAIL(ANNB_ECAPACITY, "The number of elements exceeds the specified limit");
   if (num_threads <= 0) num_threads = (int)std::thread::hardware_concurrency();
+  if (fresh != n) num_threads = 1;  // updates of stored points rewrite neighbourhoods: keep them sequential
   if (num_threads < 1) num_threads = 1;
   // "avoid using threads when the number of searches is small": hnsw_bindings.cpp:242-245
   if (n <= (int64_t)num_threads * 4) num_threads = 1;

@@ -145,6 +145,19 @@ class AnnLite:
     def search_by_vectors(self, query_np, filter=None, limit: int = 10, **kwargs):
         return self.search_numpy(query_np, filter=filter, limit=limit)
 
+    def update(self, docs, ids=None, num_threads: int = -1, **kwargs):
+        """annlite/index.py:297-332 -> CellContainer.update (container.py:323-386): stored ids are re-added, which
+        the graph handles as an in-place update (hnswalg.h:1119-1131); unknown ids are inserted."""
+        x, doc_ids = self._embeddings(docs)
+        if ids is None:
+            ids = doc_ids
+        if ids is None:
+            raise ValueError('update needs the ids of the vectors')
+        self._sanity_check(x)
+        ids = np.asarray(ids, dtype=np.int64)
+        self._index.add_with_ids(x, ids, num_threads=num_threads)
+        self._n = max(self._n, int(ids.max()) + 1)
+
     def delete(self, ids, **kwargs):
         self._index.delete([int(i) for i in ids])
 

@@ -131,8 +131,8 @@ def test_argument_errors():
         e._lib.annb_search(e._h, None, None, 0, 1, 0, 1, 10, None, 0, 0, Q.ctypes.data, Q.ctypes.data, 0, None) and L.check(-1)
     rc = e._lib.annb_search(e._h, None, None, 0, 1, 0, 1, 10, None, 0, 0, Q.ctypes.data, Q.ctypes.data, 0, None)
     assert rc == L.EINVAL and b'exactly one of' in e._lib.annb_last_error()
-    with pytest.raises(RuntimeError, match='already indexed'):
-        e.add_items(X[:1], lab[:1])
+    e.add_items(X[:1], lab[:1])          # re-adding a stored label is an in-place update, not an error
+    assert e.element_count == 50
     e2 = Engine(16, 4, 16)
     with pytest.raises(L.AnnbError, match='train the PQ'):
         e2.adc_table(Q)

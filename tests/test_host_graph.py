@@ -138,8 +138,9 @@ def test_capacity_and_resize(golden):
     e.resize_index(64)
     e.add_items_with_tables(golden.codes[:11], T[:11], golden.labels[:11], num_threads=1)
     assert e.element_count == 11
-    with pytest.raises(RuntimeError, match='already indexed'):
-        e.add_items_with_tables(golden.codes[:1], T[:1], golden.labels[:1], num_threads=1)
+    # re-adding a stored label updates it in place (hnswalg.h:1119-1131): the count does not grow
+    e.add_items_with_tables(golden.codes[:1], T[:1], golden.labels[:1], num_threads=1)
+    assert e.element_count == 11
 
 
 def test_no_cpu_fallback_on_host_only_handle(golden):

@@ -206,6 +206,12 @@ def test_annlite_index_search_dump_restore(tmp_path):
     a.delete([int(i[0, 0])])
     d4, i4 = a.search(Q[:1], limit=10)
     assert int(i[0, 0]) not in i4
+    # update: move a stored vector onto a query -> it becomes that query's nearest neighbour
+    victim = int(i[1, 5])
+    a.update(Q[1:2], ids=[victim])
+    assert a.index_size == N
+    d5, i5 = a.search(Q[1:2], limit=10)
+    assert victim in i5[0][:3]
 
 
 def test_merge_kernel_matches_host_rule():
