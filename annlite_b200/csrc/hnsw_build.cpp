@@ -69,6 +69,7 @@ int HostGraph::init(int64_t max_elems, int M_, int efc, uint64_t seed_, size_t c
   if (!level0) ANNB_FAIL(ANNB_ENOMEM, "Not enough memory");
   upper.assign((size_t)max_elems, nullptr);
   levels.assign((size_t)max_elems, 0);
+  label_lookup.reserve((size_t)max_elems);  // no rehash under the insertion lock
   inited = true;
   return ANNB_OK;
 }
@@ -81,6 +82,7 @@ int HostGraph::resize(int64_t new_max) {
   level0 = nl;
   upper.resize((size_t)new_max, nullptr);
   levels.resize((size_t)new_max, 0);
+  label_lookup.reserve((size_t)new_max);
   max_elements = new_max;
   return ANNB_OK;
 }
@@ -205,6 +207,7 @@ struct FartherFirst {  // CompareByFirst, hnswalg.h:71-76
   bool operator()(const Near &a, const Near &b) const noexcept { return a.first < b.first; }
 };
 using FarHeap = std::priority_queue<Near, std::vector<Near>, FartherFirst>;
+constexpr unsigned kMaxLinks = 2048;  // maxM0 = 2*M <= 2048 (annb_init_graph limits M to 1024)
 
 inline unsigned list_count(const uint8_t *ll) {
   uint16_t c;
@@ -309,10 +312,18 @@ struct Worker {
       if ((-cur.first) > lower) break;
       cand.pop();
       const uint32_t node = cur.second;
-      SpinGuard lk(S.node_locks, node, S.threaded);  // held for the whole scan, as in the reference (:188)
-      uint8_t *ll = g.list_at(node, layer);
-      const unsigned size = list_count(ll);
-      const uint32_t *nb = list_links(ll);
+      // The reference holds the node's lock for the whole scan (:188).  With ~100 inserting threads every
+      // walk starts at the same few hub nodes, so the lock is only held to snapshot the (<= maxM0) links and
+      // the distances are evaluated outside it; single-threaded builds are unaffected (no locks at all).
+      uint32_t snap[kMaxLinks];
+      unsigned size;
+      {
+        SpinGuard lk(S.node_locks, node, S.threaded);
+        uint8_t *ll = g.list_at(node, layer);
+        size = std::min<unsigned>(list_count(ll), kMaxLinks);
+        memcpy(snap, list_links(ll), size * sizeof(uint32_t));
+      }
+      const uint32_t *nb = snap;
       for (unsigned j = 0; j < size; j++) {
         const uint32_t cid = nb[j];
         if (seen[cid] == tag) continue;
@@ -432,10 +443,15 @@ struct Worker {
         bool changed = true;
         while (changed) {
           changed = false;
-          SpinGuard lk(S.node_locks, cur_obj, S.threaded);
-          uint8_t *ll = g.list_at(cur_obj, level);
-          const unsigned size = list_count(ll);
-          const uint32_t *nb = list_links(ll);
+          uint32_t snap[kMaxLinks];
+          unsigned size;
+          {
+            SpinGuard lk(S.node_locks, cur_obj, S.threaded);
+            uint8_t *ll = g.list_at(cur_obj, level);
+            size = std::min<unsigned>(list_count(ll), kMaxLinks);
+            memcpy(snap, list_links(ll), size * sizeof(uint32_t));
+          }
+          const uint32_t *nb = snap;
           for (unsigned i = 0; i < size; i++) {
             const uint32_t c = nb[i];
             const float d = dist_to_new(c);
@@ -579,10 +595,15 @@ struct Worker {
           bool changed = true;
           while (changed) {
             changed = false;
-            SpinGuard lk(S.node_locks, cur_obj, S.threaded);
-            uint8_t *ll = g.list_at(cur_obj, level);
-            const unsigned size = list_count(ll);
-            const uint32_t *nb = list_links(ll);
+            uint32_t snap[kMaxLinks];
+            unsigned size;
+            {
+              SpinGuard lk(S.node_locks, cur_obj, S.threaded);
+              uint8_t *ll = g.list_at(cur_obj, level);
+              size = std::min<unsigned>(list_count(ll), kMaxLinks);
+              memcpy(snap, list_links(ll), size * sizeof(uint32_t));
+            }
+            const uint32_t *nb = snap;
             for (unsigned i = 0; i < size; i++) {
               const uint32_t c = nb[i];
               const float d = dist_to_new(c);
