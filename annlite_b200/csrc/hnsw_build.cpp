@@ -12,6 +12,7 @@
 //
 // The per-point ADC table comes from the GPU (K1) in batches; this file only consumes tables.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -206,7 +207,31 @@ using Near = std::pair<float, uint32_t>;
 struct FartherFirst {  // CompareByFirst, hnswalg.h:71-76
   bool operator()(const Near &a, const Near &b) const noexcept { return a.first < b.first; }
 };
-using FarHeap = std::priority_queue<Near, std::vector<Near>, FartherFirst>;
+// std::priority_queue is specified as push_back + std::push_heap / std::pop_heap + pop_back over its container;
+// this wrapper is exactly that over a vector that is REUSED between calls (clear() keeps the capacity), so an
+// insertion performs no heap allocations while its tie behaviour stays identical to the reference's queues.
+template <class Cmp>
+struct ReHeap {
+  std::vector<Near> v;
+  Cmp cmp;
+  void clear() { v.clear(); }
+  bool empty() const { return v.empty(); }
+  size_t size() const { return v.size(); }
+  const Near &top() const { return v.front(); }
+  void emplace(float d, uint32_t id) {
+    v.emplace_back(d, id);
+    std::push_heap(v.begin(), v.end(), cmp);
+  }
+  void push(const Near &n) {
+    v.push_back(n);
+    std::push_heap(v.begin(), v.end(), cmp);
+  }
+  void pop() {
+    std::pop_heap(v.begin(), v.end(), cmp);
+    v.pop_back();
+  }
+};
+using FarHeap = ReHeap<FartherFirst>;
 constexpr unsigned kMaxLinks = 2048;  // maxM0 = 2*M <= 2048 (annb_init_graph limits M to 1024)
 
 inline unsigned list_count(const uint8_t *ll) {
@@ -229,10 +254,24 @@ struct SpinLocks {
     n = m;
   }
   void lock(size_t i) {
+    // A node can stay locked for a whole insertion (~1 ms, see Worker::insert), so waiters back off:
+    // a short busy phase, then yields, then sleeps -- 100+ inserting threads must not burn their
+    // hyper-thread siblings' cycles while they wait.
+    int spins = 0;
     for (;;) {
       uint8_t e = 0;
       if (f[i].compare_exchange_weak(e, 1, std::memory_order_acquire)) return;
-      while (f[i].load(std::memory_order_relaxed)) std::this_thread::yield();
+      while (f[i].load(std::memory_order_relaxed)) {
+        if (++spins < 64) {
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        } else if (spins < 96) {
+          std::this_thread::yield();
+        } else {
+          std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+      }
     }
   }
   void unlock(size_t i) { f[i].store(0, std::memory_order_release); }
@@ -261,8 +300,12 @@ struct SharedBuild {
 struct Worker {
   SharedBuild &S;
   HostGraph &g;
-  std::vector<uint32_t> seen;  // visited tags (hnswlib/visited_list_pool.h:10-30)
-  uint32_t tag = 0;
+  std::vector<uint16_t> seen;  // visited tags, 16-bit like vl_type (hnswlib/visited_list_pool.h:8-30)
+  uint16_t tag = 0;
+  FarHeap h_top, h_cand, h_cands, h_filtered;  // reused across insertions
+  ReHeap<std::less<Near>> h_closest;
+  std::vector<Near> kept;
+  std::vector<uint32_t> sel;
   const float *T = nullptr;  // ADC table of the point being inserted (n_sub x Ks)
 
   explicit Worker(SharedBuild &s) : S(s), g(*s.g) {}
@@ -292,9 +335,11 @@ struct Worker {
   }
 
   // searchBaseLayer(ep, point, layer): hnswalg.h:158-238
-  FarHeap search_layer(uint32_t ep, int layer) {
+  void search_layer(uint32_t ep, int layer, FarHeap &top) {
     next_tag();
-    FarHeap top, cand;
+    FarHeap &cand = h_cand;
+    top.clear();
+    cand.clear();
     const size_t efc = (size_t)g.ef_construction;
     float lower;
     if (!g.deleted(ep)) {
@@ -337,15 +382,15 @@ struct Worker {
         }
       }
     }
-    return top;
   }
 
   // getNeighborsByHeuristic2(top_candidates, M): hnswalg.h:443-483.  In PQ mode the pairwise
   // distance inside the loop is dist_to_new(current).
   void select_neighbors(FarHeap &top, size_t Mlim) {
     if (top.size() < Mlim) return;
-    std::priority_queue<Near> closest;  // default less<pair>: (-(dist), id) lexicographic
-    std::vector<Near> kept;
+    auto &closest = h_closest;  // default less<pair>: (-(dist), id) lexicographic
+    closest.clear();
+    kept.clear();
     while (!top.empty()) {
       closest.emplace(-top.top().first, top.top().second);
       top.pop();
@@ -369,8 +414,7 @@ struct Worker {
     const size_t Mcurmax = level ? (size_t)g.maxM : (size_t)g.maxM0;
     select_neighbors(top, (size_t)g.M);
     if (top.size() > (size_t)g.M) ANNB_FAIL(ANNB_EINVAL, "Should be not be more than M_ candidates returned by the heuristic");
-    std::vector<uint32_t> sel;
-    sel.reserve((size_t)g.M);
+    sel.clear();
     while (!top.empty()) {
       sel.push_back(top.top().second);
       top.pop();
@@ -411,7 +455,8 @@ struct Worker {
       } else {
         // "finding the weakest element": in PQ mode every distance below is dist_to_new(other)
         const float d_max = dist_to_new(other);
-        FarHeap cands;
+        FarHeap &cands = h_cands;
+        cands.clear();
         cands.emplace(d_max, cur);
         for (size_t j = 0; j < sz; j++) cands.emplace(dist_to_new(other), data[j]);
         select_neighbors(cands, Mcurmax);
@@ -466,8 +511,10 @@ struct Worker {
     }
     if (elem_level > max_level) ANNB_FAIL(ANNB_EINVAL, "Level of item to be updated cannot be bigger than max level");
     for (int level = elem_level; level >= 0; level--) {
-      FarHeap top = search_layer(cur_obj, level);
-      FarHeap filtered;
+      FarHeap &top = h_top;
+      search_layer(cur_obj, level, top);
+      FarHeap &filtered = h_filtered;
+      filtered.clear();
       while (!top.empty()) {
         if (top.top().second != id) filtered.push(top.top());
         top.pop();
@@ -505,7 +552,8 @@ struct Worker {
         for (uint32_t h2 : connections(h1, layer)) s_cand.insert(h2);
       }
       for (uint32_t neigh : s_neigh) {
-        FarHeap cands;
+        FarHeap &cands = h_cands;
+        cands.clear();
         const size_t size = s_cand.find(neigh) == s_cand.end() ? s_cand.size() : s_cand.size() - 1;
         const size_t keep = std::min((size_t)g.ef_construction, size);
         for (uint32_t c : s_cand) {
@@ -567,6 +615,8 @@ struct Worker {
       g.count.store(cur + 1);
       g.label_lookup[label] = cur;
     }
+    // held for the whole insertion like link_list_locks_[cur_c] in the reference (:1144): until every level of
+    // `cur` is linked, no other thread may append itself to one of its still-blank lists
     SpinGuard self(S.node_locks, cur, S.threaded);
     const int curlevel = random_level();
     g.levels[cur] = curlevel;
@@ -618,7 +668,8 @@ struct Worker {
       }
       const bool ep_deleted = g.deleted(ep_copy);
       for (int level = std::min(curlevel, maxlevelcopy); level >= 0; level--) {
-        FarHeap top = search_layer(cur_obj, level);
+        FarHeap &top = h_top;
+        search_layer(cur_obj, level, top);
         if (ep_deleted) {
           top.emplace(dist_to_new(ep_copy), ep_copy);
           if (top.size() > (size_t)g.ef_construction) top.pop();
