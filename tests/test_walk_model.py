@@ -1,0 +1,155 @@
+"""CPU: executable statement of the two equivalence arguments the CUDA walks rest on.
+
+A plain-Python model of (1) the single-list, visited-free walk (hnsw_walk_fast) and (2) the flagged
+single-list walk for filters / deletions (hnsw_walk_flagged) is run against the oracle -- which is
+bit-identical to the reference's two-heap + visited-array search -- on the committed fixtures.  The models
+use no visited set and no candidate heap; they must return the same ids, distances AND the same number of
+hops (every expansion the reference makes, the model makes)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+FLT_MAX = np.float32(3.4028234663852886e+38)
+
+
+class G:
+    def __init__(self, g):
+        self.g = g
+        self.cnt, self.lk, self.dele = g.links0()
+        self.codes = g.codes()
+        self.labels = g.labels()
+
+    def dist(self, t, i):
+        r = np.float32(0)
+        for m in range(self.g.M_sub):
+            r = np.float32(r + t[m, self.codes[i, m]])
+        return r
+
+    def descend(self, t):
+        g = self.g
+        cur, cd, hops = g.enterpoint, self.dist(t, g.enterpoint), 0
+        for level in range(g.maxlevel, 0, -1):
+            changed = True
+            while changed:
+                changed, hops = False, hops + 1
+                o = int(g.link_off[cur]) + (level - 1) * g.size_links_per_elem
+                c = int(np.frombuffer(g.links[o:o + 2].tobytes(), dtype=np.uint16)[0])
+                for x in np.frombuffer(g.links[o + 4:o + 4 + 4 * c].tobytes(), dtype=np.uint32):
+                    d = self.dist(t, int(x))
+                    if d < cd:
+                        cd, cur, changed = d, int(x), True
+        return cur, cd, hops
+
+
+def walk_single_list(G_, t, k, ef):
+    """hnsw_walk_fast: ONE sorted list of <= ef (d, id, expanded); no visited set, no candidate heap."""
+    cur, cd, hops = G_.descend(t)
+    L = [(cd, cur, True)]
+    node = cur
+    while True:
+        hops += 1
+        worst = L[ef - 1][0] if len(L) >= ef else np.float32(np.inf)
+        listed = {e[1] for e in L}
+        for j in range(G_.cnt[node]):
+            x = int(G_.lk[node, j])
+            d = G_.dist(t, x)
+            if d < worst and x not in listed:                 # admission (:306) + "still listed" check
+                pos = sum(1 for e in L if e[0] <= d)           # after equal keys, arrival order
+                L.insert(pos, (d, x, False))
+                listed.add(x)
+        L = L[:ef]                                             # the tail beyond ef falls off
+        nxt = next((i for i, e in enumerate(L) if not e[2]), None)
+        if nxt is None:
+            break
+        node = L[nxt][1]
+        L[nxt] = (L[nxt][0], node, True)
+    top = L[:k]
+    return np.array([G_.labels[e[1]] for e in top], dtype=np.uint64), np.array([e[0] for e in top], dtype=np.float32), hops
+
+
+def walk_flagged(G_, t, k, ef, passes, use_filter, has_del):
+    """hnsw_walk_flagged: one list of every candidate with a PASS flag; lowerBound read off the list."""
+    cur, cd, hops = G_.descend(t)
+    p0 = passes(cur)
+    L = [(cd, cur, True, p0)]
+    lb = cd if p0 else FLT_MAX
+    npass = 1 if p0 else 0
+    node = cur
+    while True:
+        hops += 1
+        listed = {e[1] for e in L}
+        for j in range(G_.cnt[node]):
+            x = int(G_.lk[node, j])
+            d = G_.dist(t, x)
+            if (npass < ef or d < lb) and x not in listed:     # :306 / :413 against the hop-start lowerBound
+                pos = sum(1 for e in L if e[0] <= d)
+                L.insert(pos, (d, x, False, passes(x)))
+                listed.add(x)
+        idx = [i for i, e in enumerate(L) if e[3]]
+        if len(idx) >= ef:
+            L = L[:idx[ef - 1] + 1]                            # everything behind the ef-th passing entry is dead
+            npass, lb = ef, L[-1][0]
+        else:
+            npass = len(idx)
+            if idx:
+                lb = L[idx[-1]][0]
+        nxt = next((i for i, e in enumerate(L) if not e[2]), None)
+        if nxt is None:
+            break
+        key = L[nxt][0]
+        if use_filter:
+            if key > lb:
+                break                                          # :371
+        elif key > lb and (npass == ef or not has_del):
+            break                                              # :270
+        node = L[nxt][1]
+        L[nxt] = (L[nxt][0], node, True, L[nxt][3])
+    top = [e for e in L if e[3]][:k]
+    return np.array([G_.labels[e[1]] for e in top], dtype=np.uint64), np.array([e[0] for e in top], dtype=np.float32), hops
+
+
+NQ = 12
+
+
+def _same(l, d, rl, rd):
+    order = np.lexsort((l, d))                 # rows come back ascending (dist, label)
+    return np.array_equal(l[order], rl) and np.array_equal(d[order].view(np.uint32), rd.view(np.uint32))
+
+
+def test_single_list_walk_equals_two_heap_walk(golden):
+    g = golden.oracle_graph()
+    t = golden.query_tables_oracle()[:NQ]
+    rl, rd, found, (hops, nbrs, evals) = O.hnsw_search(g, t, golden.k, golden.ef, with_counts=True)
+    M = G(g)
+    bad = 0
+    for b in range(NQ):
+        l, d, h = walk_single_list(M, t[b], golden.k, golden.ef)
+        ok = _same(l, d, rl[b], rd[b]) and h == hops[b]
+        bad += not ok
+    assert bad <= (3 if golden.name == 'ties_k16' else 0)      # only exact fp32 ties may differ
+
+
+def test_flagged_walk_equals_filtered_two_heap_walk(golden):
+    g = golden.oracle_graph()
+    t = golden.query_tables_oracle()[:NQ]
+    rl, rd, found, (hops, _, _) = O.hnsw_search(g, t, golden.k, golden.ef, filter_labels=golden.allow, with_counts=True)
+    M = G(g)
+    allowed = set(golden.allow.tolist())
+    bad = 0
+    for b in range(NQ):
+        l, d, h = walk_flagged(M, t[b], golden.k, golden.ef, lambda i: int(M.labels[i]) in allowed, True, False)
+        bad += not (_same(l, d, rl[b], rd[b]) and h == hops[b])
+    assert bad <= (3 if golden.name == 'ties_k16' else 0)
+
+
+def test_flagged_walk_equals_deletion_aware_two_heap_walk(golden):
+    g = golden.oracle_graph(deleted=True)
+    t = golden.query_tables_oracle()[:NQ]
+    rl, rd, found, (hops, _, _) = O.hnsw_search(g, t, golden.k, golden.ef, with_counts=True)
+    M = G(g)
+    bad = 0
+    for b in range(NQ):
+        l, d, h = walk_flagged(M, t[b], golden.k, golden.ef, lambda i: not M.dele[i], False, True)
+        bad += not (_same(l, d, rl[b], rd[b]) and h == hops[b])
+    assert bad <= (3 if golden.name == 'ties_k16' else 0)
