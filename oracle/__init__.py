@@ -190,11 +190,13 @@ class Graph:
         return cnt, lk, dele
 
 
-def hnsw_search(g: Graph, tables, k, ef, filter_labels=None, with_counts=False):
+def hnsw_search(g: Graph, tables, k, ef, filter_labels=None, with_counts=False, with_ties=False):
     """searchKnn / searchKnnWithFilter over `g` for a (B,M,Ks) batch of tables.
 
     Returns (labels uint64 (B,k), dists fp32 (B,k), found int32 (B,)) [+ (hops, nbrs, evals)].
     ``filter_labels``: iterable of allowed labels (what the reference receives as ``filters``).
+    ``with_ties``: append an int64 (B,) count of exact-fp32-tie events met by each walk (see
+    ``orc_set_tie_sink`` in pq_oracle.c) -- rows with 0 leave no freedom at all to an implementation.
     """
     tables = np.ascontiguousarray(tables, dtype=np.float32)
     B = tables.shape[0]
@@ -209,11 +211,35 @@ def hnsw_search(g: Graph, tables, k, ef, filter_labels=None, with_counts=False):
         fl = np.asarray(filter_labels, dtype=np.uint64)
         member = np.isin(g.labels(), fl)          # membership is by label; the C side tests by internal id
         bm = np.packbits(np.concatenate([member, np.zeros(8, dtype=bool)]), bitorder='little')
+    ties = np.zeros(B, dtype=np.int64)
+    lib().orc_set_tie_sink(_p(ties) if with_ties else None)
     lib().orc_hnsw_search(_p(g.level0), C.c_uint64(g.size_per_elem), C.c_uint64(g.offset_data),
                           C.c_uint64(g.label_offset), _p(g.links), _p(g.link_off), _p(g.levels),
                           C.c_uint64(g.size_links_per_elem), C.c_int64(g.n), C.c_int32(g.maxlevel),
                           C.c_uint32(g.enterpoint), g.M_sub, g.Ks, g.code_bytes, _p(tables), C.c_int64(B),
                           int(k), int(ef), _p(bm), _p(labels), _p(dists), _p(found), _p(hops), _p(nbrs), _p(evals))
+    lib().orc_set_tie_sink(None)
+    out = (labels, dists, found)
     if with_counts:
-        return labels, dists, found, (hops, nbrs, evals)
-    return labels, dists, found
+        out += ((hops, nbrs, evals),)
+    if with_ties:
+        out += (ties,)
+    return out
+
+
+def single_list_walk(g: Graph, tables, k, ef):
+    """NOT the reference: the scalar model of the product's visited-free single-list walk
+    (``orc_single_list_walk`` in pq_oracle.c).  Returns (labels, dists, found, hops, nbrs)."""
+    tables = np.ascontiguousarray(tables, dtype=np.float32)
+    B = tables.shape[0]
+    labels = np.empty((B, k), dtype=np.uint64)
+    dists = np.empty((B, k), dtype=np.float32)
+    found = np.zeros(B, dtype=np.int32)
+    hops = np.zeros(B, dtype=np.int64)
+    nbrs = np.zeros(B, dtype=np.int64)
+    lib().orc_single_list_walk(_p(g.level0), C.c_uint64(g.size_per_elem), C.c_uint64(g.offset_data),
+                               C.c_uint64(g.label_offset), _p(g.links), _p(g.link_off), _p(g.levels),
+                               C.c_uint64(g.size_links_per_elem), C.c_int64(g.n), C.c_int32(g.maxlevel),
+                               C.c_uint32(g.enterpoint), g.M_sub, g.Ks, g.code_bytes, _p(tables), C.c_int64(B),
+                               int(k), int(ef), _p(labels), _p(dists), _p(found), _p(hops), _p(nbrs))
+    return labels, dists, found, hops, nbrs

@@ -19,6 +19,7 @@
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */
 #include <float.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -202,8 +203,18 @@ typedef struct { pq_t top, cand; uint32_t *visited; uint32_t tag; } ws_t;
  * the Python wrapper for every node whose *label* is in the caller's list; the
  * reference tests binary_fuse16_contain(label), an approximate set with ~2^-16 false positives;
  * the exact bitmap is what that filter approximates -- SURVEY.md section 2 row 6). */
+/* Test aid: where an exact fp32 tie leaves the reference's outcome to heap order, the GPU walk (which
+ * keeps arrival order among equal keys) is free to differ; tests ask for the per-query count of such
+ * events so that they can tell "differs at a tie" from "differs".  Two events are counted:
+ *  - an entry is evicted from top_candidates while an equal key stays behind as the new lowerBound
+ *    (the evicted node is still expanded by the reference because its distance is not > lowerBound);
+ *  - two candidates with equal distance are next to each other at the top of candidate_set. */
+static int64_t *g_tie_sink = 0;
+ORC_API void orc_set_tie_sink(int64_t *sink) { g_tie_sink = sink; }
+
 static void search_base(const graph_t *g, const float *table, uint32_t ep, size_t ef, int has_del,
-                        const uint8_t *filter, ws_t *w, int64_t *hops, int64_t *nbrs, int64_t *evals) {
+                        const uint8_t *filter, ws_t *w, int64_t *hops, int64_t *nbrs, int64_t *evals,
+                        int64_t *ties) {
   w->top.n = w->cand.n = 0;
   w->tag++;
   float lower;
@@ -224,6 +235,7 @@ static void search_base(const graph_t *g, const float *table, uint32_t ep, size_
     if (filter) { if ((-cur.d) > lower) break; }                                   /* :371 */
     else if ((-cur.d) > lower && (w->top.n == ef || !has_del)) break;              /* :270 */
     pq_pop(&w->cand);
+    if (ties && w->cand.n && w->cand.a[0].d == cur.d) (*ties)++;
     const uint8_t *ll = g_list(g, cur.id, 0);
     unsigned size = g_count(ll);
     (*hops)++;
@@ -240,7 +252,11 @@ static void search_base(const graph_t *g, const float *table, uint32_t ep, size_
         if (filter) admit = (filter[cid >> 3] >> (cid & 7)) & 1;                                /* :423-426 */
         else admit = !has_del || !g_deleted(g, cid);                                            /* :314 */
         if (admit) pq_push(&w->top, d, cid);
-        if (w->top.n > ef) pq_pop(&w->top);
+        if (w->top.n > ef) {
+          float gone = w->top.a[0].d;
+          pq_pop(&w->top);
+          if (ties && w->top.n && w->top.a[0].d == gone) (*ties)++;
+        }
         if (w->top.n) lower = w->top.a[0].d;
       }
     }
@@ -301,8 +317,13 @@ ORC_API int orc_hnsw_search(const uint8_t *level0, uint64_t size_per_elem, uint6
         }
       }
     }
-    search_base(&g, t, cur, ef, has_del, filter, &w, &hops, &nbrs, &evals);
-    while (w.top.n > (size_t)k) pq_pop(&w.top);                                    /* :1286-1288 */
+    int64_t ties = 0;
+    search_base(&g, t, cur, ef, has_del, filter, &w, &hops, &nbrs, &evals, g_tie_sink ? &ties : 0);
+    while (w.top.n > (size_t)k) {                                                  /* :1286-1288 */
+      float gone = w.top.a[0].d;
+      pq_pop(&w.top);
+      if (g_tie_sink && w.top.n && w.top.a[0].d == gone) ties++;    /* a tie at the k-th place */
+    }
     int cnt = (int)w.top.n;
     for (int i = 0; i < cnt; i++) { res[i].d = w.top.a[i].d; res[i].l = g_label(&g, w.top.a[i].id); }
     qsort(res, (size_t)cnt, sizeof(res_t), res_cmp);
@@ -311,6 +332,7 @@ ORC_API int orc_hnsw_search(const uint8_t *level0, uint64_t size_per_elem, uint6
       out_labels[(size_t)b * k + i] = i < cnt ? res[i].l : UINT64_MAX;
     }
     found[b] = cnt;
+    if (g_tie_sink) g_tie_sink[b] = ties;
     if (out_hops) out_hops[b] = hops;
     if (out_nbrs) out_nbrs[b] = nbrs;
     if (out_evals) out_evals[b] = evals;
@@ -348,4 +370,91 @@ ORC_API void orc_encode(const float *x, const float *cb, int64_t N, int M, int K
       else if (code_bytes == 2) ((uint16_t *)out)[o] = (uint16_t)arg;
       else ((uint32_t *)out)[o] = arg;
     }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * NOT the reference's algorithm: a scalar model of the product's single-list walk (hnsw_walk_fast in
+ * annlite_b200/csrc/hnsw_search.cu -- one sorted list of at most ef (distance, node, expanded) entries,
+ * no visited set, no candidate heap, arrival order among equal keys).  CPU tests run it beside
+ * orc_hnsw_search to check the equivalence argument of DESIGN.md section 4 at sizes where a Python model
+ * is too slow, including which rows an exact fp32 tie may change.  Measured against the B200: on the
+ * dumps of scripts/repro_shapes.py it reproduces the kernel's result sets and hop counts row for row.
+ * Same arguments as orc_hnsw_search without filter; rows come back ascending by (dist, label).        */
+ORC_API int orc_single_list_walk(const uint8_t *level0, uint64_t size_per_elem, uint64_t offset_data,
+                                 uint64_t label_offset, const uint8_t *links, const uint64_t *link_off,
+                                 const int32_t *levels, uint64_t size_links_per_elem, int64_t n,
+                                 int32_t maxlevel, uint32_t enterpoint, int M, int Ks, int code_bytes,
+                                 const float *tables, int64_t B, int k, int ef_, uint64_t *out_labels,
+                                 float *out_dists, int32_t *found, int64_t *out_hops, int64_t *out_nbrs) {
+  graph_t g = {level0, size_per_elem, offset_data, label_offset, links, link_off, levels,
+               size_links_per_elem, n, maxlevel, enterpoint, M, Ks, code_bytes};
+  if (n == 0) { for (int64_t b = 0; b < B; b++) found[b] = 0; return 0; }
+  const int ef = ef_ > k ? ef_ : k;
+  float *K = (float *)malloc(sizeof(float) * (size_t)(ef + 1));
+  uint32_t *V = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(ef + 1));
+  uint8_t *X = (uint8_t *)malloc((size_t)(ef + 1));
+  res_t *res = (res_t *)malloc(sizeof(res_t) * (size_t)(ef + 1));
+  for (int64_t b = 0; b < B; b++) {
+    const float *t = tables + (size_t)b * M * Ks;
+    int64_t hops = 0, nbrs = 0;
+    uint32_t cur = enterpoint;
+    float curdist = pq_lookup(t, M, Ks, g_code(&g, cur), code_bytes);
+    for (int level = maxlevel; level > 0; level--) {
+      int changed = 1;
+      while (changed) {
+        changed = 0;
+        const uint8_t *ll = g_list(&g, cur, level);
+        unsigned size = g_count(ll);
+        hops++;
+        nbrs += size;
+        for (unsigned i = 0; i < size; i++) {
+          uint32_t cand = g_link(ll, i);
+          float d = pq_lookup(t, M, Ks, g_code(&g, cand), code_bytes);
+          if (d < curdist) { curdist = d; cur = cand; changed = 1; }
+        }
+      }
+    }
+    int size = 1;
+    K[0] = curdist; V[0] = cur; X[0] = 1;
+    uint32_t node = cur;
+    for (;;) {
+      const uint8_t *ll = g_list(&g, node, 0);
+      unsigned cnt = g_count(ll);
+      hops++;
+      nbrs += cnt;
+      const float worst = size >= ef ? K[ef - 1] : HUGE_VALF;     /* lowerBound as of the hop's start */
+      for (unsigned j = 0; j < cnt; j++) {
+        uint32_t x = g_link(ll, j);
+        float d = pq_lookup(t, M, Ks, g_code(&g, x), code_bytes);
+        if (!(d < worst)) continue;
+        int pos = 0, dup = 0;
+        while (pos < size && K[pos] <= d) pos++;                  /* after its equals */
+        for (int i = pos - 1; i >= 0 && K[i] == d; i--) if (V[i] == x) { dup = 1; break; }
+        if (dup || pos >= ef) continue;
+        int ns = size < ef ? size + 1 : ef;
+        memmove(K + pos + 1, K + pos, sizeof(float) * (size_t)(ns - 1 - pos));
+        memmove(V + pos + 1, V + pos, sizeof(uint32_t) * (size_t)(ns - 1 - pos));
+        memmove(X + pos + 1, X + pos, (size_t)(ns - 1 - pos));
+        K[pos] = d; V[pos] = x; X[pos] = 0;
+        size = ns;
+      }
+      int nx = -1;
+      for (int i = 0; i < size; i++) if (!X[i]) { nx = i; break; }
+      if (nx < 0) break;
+      X[nx] = 1;
+      node = V[nx];
+    }
+    int cnt = size < k ? size : k;
+    for (int i = 0; i < cnt; i++) { res[i].d = K[i]; res[i].l = g_label(&g, V[i]); }
+    qsort(res, (size_t)cnt, sizeof(res_t), res_cmp);
+    for (int i = 0; i < k; i++) {
+      out_dists[(size_t)b * k + i] = i < cnt ? res[i].d : FLT_MAX;
+      out_labels[(size_t)b * k + i] = i < cnt ? res[i].l : UINT64_MAX;
+    }
+    found[b] = cnt;
+    if (out_hops) out_hops[b] = hops;
+    if (out_nbrs) out_nbrs[b] = nbrs;
+  }
+  free(K); free(V); free(X); free(res);
+  return 0;
 }

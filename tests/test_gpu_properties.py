@@ -128,11 +128,12 @@ def test_oracle_agrees_on_a_sample(big):
     g = O.Graph.from_state(e.get_graph(), M, KS)
     q = big['Q'][:200]
     t = O.adc_table(q, big['cb'])
-    ol, od, _, (hops, nbrs, _) = O.hnsw_search(g, t, 10, 64, with_counts=True)
+    ol, od, _, (hops, nbrs, _), ties = O.hnsw_search(g, t, 10, 64, with_counts=True, with_ties=True)
     l, d, st = e.search(queries=q, k=10, ef=64, with_stats=True)
     same = (l == ol).all(1)
-    assert same.mean() >= 0.99
+    assert same.mean() >= 0.99 and same[ties == 0].all()
     assert np.array_equal(bits(d[same]), bits(od[same]))
+    same &= ties == 0                     # a tie the reference resolved by heap order can cost/save a hop
     assert np.array_equal(st[same, 0], hops[same]) and np.array_equal(st[same, 1], nbrs[same])
 
 

@@ -37,12 +37,17 @@ def check(e, g, cb, Qn, metric, k, ef, filt=None, strict=True):
     dev_t = e.adc_table(Qn, normalize=0)
     assert np.array_equal(bits(dev_t), bits(t))
     l, d, st = e.search(tables=t, k=k, ef=ef, filter_labels=filt, with_stats=True)
-    ol, od, found, (hops, nbrs, evals) = O.hnsw_search(g, t, k, ef, filter_labels=filt, with_counts=True)
+    ol, od, found, (hops, nbrs, evals), ties = O.hnsw_search(g, t, k, ef, filter_labels=filt, with_counts=True, with_ties=True)
     assert (found == k).all()
-    v = tie_aware_rows(l, d, ol, od)
-    assert v.count('diff') == 0, (v.count('exact'), v.count('tie'), v.count('diff'))
-    same = np.array([x == 'exact' for x in v])
-    assert np.array_equal(st[same, 0], hops[same]) and np.array_equal(st[same, 1], nbrs[same])
+    v = np.array(tie_aware_rows(l, d, ol, od))
+    # A walk that met no exact fp32 tie leaves no freedom: ids, distance bits, hop and neighbour counts all equal.
+    # Where the oracle met a tie (its outcome then hangs on std::priority_queue's heap order) the GPU walk, which
+    # keeps arrival order among equal keys, may expand one node more or fewer; its results must still agree up to
+    # ties in all but a stray row (about 1 walk in 10^4 at ef >= 128 on this data, scripts/repro_shapes.py).
+    clean = ties == 0
+    assert (v[clean] == 'exact').all(), (v[clean] != 'exact').sum()
+    assert np.array_equal(st[clean, 0], hops[clean]) and np.array_equal(st[clean, 1], nbrs[clean])
+    assert (v[~clean] == 'diff').sum() <= 1, ((v == 'exact').sum(), (v == 'tie').sum(), (v == 'diff').sum())
 
 
 def test_c3_like_m32_d768_k100():

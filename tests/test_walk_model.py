@@ -153,3 +153,32 @@ def test_flagged_walk_equals_deletion_aware_two_heap_walk(golden):
         l, d, h = walk_flagged(M, t[b], golden.k, golden.ef, lambda i: not M.dele[i], False, True)
         bad += not (_same(l, d, rl[b], rd[b]) and h == hops[b])
     assert bad <= (3 if golden.name == 'ties_k16' else 0)
+
+
+# ---- the same equivalence at the sizes the GPU shape tests use, through the scalar C model ---------------
+def _host_built(N, D, M, Ks, seed, threads, Mconn=16, efc=100):
+    from annlite_b200.engine import Engine
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((256, D)).astype(np.float32)
+    ds = D // M
+    cb = np.stack([X[rng.choice(N, Ks, replace=False), m * ds:(m + 1) * ds] for m in range(M)]).astype(np.float32)
+    e = Engine(D, M, Ks, 'euclidean', device=-1)          # host-only handle: graph building needs no GPU
+    e.init_graph(N, M=Mconn, ef_construction=efc)
+    e.add_items_with_tables(O.encode(X, cb), O.adc_table(X, cb), np.arange(N, dtype=np.uint64) + 11, num_threads=threads)
+    return O.Graph.from_state(e.get_graph(), M, Ks), O.adc_table(Q, cb)
+
+
+@pytest.mark.parametrize('shape', [(20000, 96, 16, 256, 5, 16), (6000, 768, 32, 256, 3, 16), (5000, 64, 8, 300, 7, 16), (4000, 32, 8, 256, 11, 24)])
+def test_single_list_model_vs_oracle_at_gpu_test_shapes(shape):
+    from helpers import tie_aware_rows
+    N, D, M, Ks, seed, Mconn = shape
+    g, t = _host_built(N, D, M, Ks, seed, threads=8, Mconn=Mconn)
+    for k, ef in ((10, 64), (10, 256), (100, 128)):
+        ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t, k, ef, with_counts=True, with_ties=True)
+        ml, md, mf, mh, mn = O.single_list_walk(g, t, k, ef)
+        v = np.array(tie_aware_rows(ml, md, ol, od))
+        clean = ties == 0
+        assert (v[clean] == 'exact').all()
+        assert np.array_equal(mh[clean], hops[clean]) and np.array_equal(mn[clean], nbrs[clean])
+        assert (v[~clean] == 'diff').sum() <= 1
