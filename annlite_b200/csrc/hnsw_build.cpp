@@ -18,6 +18,7 @@
 #include <cstring>
 #include <queue>
 #include <random>
+#include <sched.h>
 #include <thread>
 #include <unordered_set>
 
@@ -691,6 +692,45 @@ struct Worker {
 
 }  // namespace
 
+// Default insertion thread count (num_threads <= 0; the reference takes hardware_concurrency(),
+// hnsw_bindings.cpp:239-240).  The CPUs this process may actually run on are the smaller of the
+// affinity mask and the cgroup CPU quota -- a container that reports 128 logical CPUs but is
+// throttled to a fraction of them turns every held node lock into a convoy.  Capped at 32: on the
+// 2 x 64-thread hosts of the B200 boxes the 1M-point build took 27 s with 32 threads, 34 s with
+// 64 and 56 s with 128; callers that know better pass num_threads.
+int hnsw_default_threads() {
+  int n = (int)std::thread::hardware_concurrency();
+  if (n < 1) n = 1;
+#if defined(__linux__)
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int a = CPU_COUNT(&set);
+    if (a > 0 && a < n) n = a;
+  }
+  long long quota = -1, period = -1;
+  if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+    char q[32] = {0};
+    if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0) quota = atoll(q);
+    fclose(f);
+  } else {
+    if (FILE *fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+      if (fscanf(fq, "%lld", &quota) != 1) quota = -1;
+      fclose(fq);
+    }
+    if (FILE *fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+      if (fscanf(fp, "%lld", &period) != 1) period = -1;
+      fclose(fp);
+    }
+  }
+  if (quota > 0 && period > 0) {
+    const int c = (int)((quota + period - 1) / period);
+    if (c >= 1 && c < n) n = c;
+  }
+#endif
+  return n < 32 ? n : 32;
+}
+
 // Inserts rows [0, n) whose ADC tables are produced chunk-wise by `table_chunk(first, count)`
 // (host pointer to count*M*Ks floats valid until the next call) -- see capi.cu.
 int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels, int64_t n, int num_threads,
@@ -704,7 +744,7 @@ int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels
       if (g.label_lookup.find(labels[i]) == g.label_lookup.end() && seen_in_batch.insert(labels[i]).second) fresh++;
   }
   if (g.count.load() + fresh > g.max_elements) ANNB_FAIL(ANNB_ECAPACITY, "The number of elements exceeds the specified limit");
-  if (num_threads <= 0) num_threads = (int)std::thread::hardware_concurrency();
+  if (num_threads <= 0) num_threads = hnsw_default_threads();
   if (fresh != n) num_threads = 1;  // updates of stored points rewrite neighbourhoods: keep them sequential
   if (num_threads < 1) num_threads = 1;
   // "avoid using threads when the number of searches is small": hnsw_bindings.cpp:242-245

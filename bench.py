@@ -209,7 +209,7 @@ def run_ours(a):
             X = make_base(a, lo, hi)
             e.init_graph(hi - lo, M=a.M, ef_construction=a.efc)
             t0 = time.time()
-            e.add_items(X, np.arange(lo, hi, dtype=np.uint64), num_threads=a.build_threads or max(1, ncores // world))
+            e.add_items(X, np.arange(lo, hi, dtype=np.uint64), num_threads=a.build_threads or min(32, max(1, ncores // world)))
             t_build = time.time() - t0
             e.save_index(path)
             del X
@@ -219,7 +219,7 @@ def run_ours(a):
             X = make_base(a)
             e.init_graph(a.n, M=a.M, ef_construction=a.efc)
             t0 = time.time()
-            e.add_items(X, np.arange(a.n, dtype=np.uint64), num_threads=a.build_threads or ncores)
+            e.add_items(X, np.arange(a.n, dtype=np.uint64), num_threads=a.build_threads)   # 0 = library default (<= 32, quota-aware)
             t_build = time.time() - t0
             e.save_index(path + '.tmp')
             os.replace(path + '.tmp', path)
