@@ -243,3 +243,26 @@ def single_list_walk(g: Graph, tables, k, ef):
                                C.c_uint32(g.enterpoint), g.M_sub, g.Ks, g.code_bytes, _p(tables), C.c_int64(B),
                                int(k), int(ef), _p(labels), _p(dists), _p(found), _p(hops), _p(nbrs))
     return labels, dists, found, hops, nbrs
+
+
+def flagged_walk(g: Graph, tables, k, ef, filter_labels=None, cap=512):
+    """NOT the reference: the scalar model of the product's flagged single-list walk (filters / deletions),
+    ``orc_flagged_walk`` in pq_oracle.c.  Returns (labels, dists, found (-1 = capacity overflow), hops, nbrs, peak)."""
+    tables = np.ascontiguousarray(tables, dtype=np.float32)
+    B = tables.shape[0]
+    labels = np.empty((B, k), dtype=np.uint64)
+    dists = np.empty((B, k), dtype=np.float32)
+    found = np.zeros(B, dtype=np.int32)
+    hops = np.zeros(B, dtype=np.int64)
+    nbrs = np.zeros(B, dtype=np.int64)
+    peak = np.zeros(B, dtype=np.int32)
+    bm = None
+    if filter_labels is not None:
+        member = np.isin(g.labels(), np.asarray(filter_labels, dtype=np.uint64))
+        bm = np.packbits(np.concatenate([member, np.zeros(8, dtype=bool)]), bitorder='little')
+    lib().orc_flagged_walk(_p(g.level0), C.c_uint64(g.size_per_elem), C.c_uint64(g.offset_data),
+                           C.c_uint64(g.label_offset), _p(g.links), _p(g.link_off), _p(g.levels),
+                           C.c_uint64(g.size_links_per_elem), C.c_int64(g.n), C.c_int32(g.maxlevel),
+                           C.c_uint32(g.enterpoint), g.M_sub, g.Ks, g.code_bytes, _p(tables), C.c_int64(B),
+                           int(k), int(ef), _p(bm), int(cap), _p(labels), _p(dists), _p(found), _p(hops), _p(nbrs), _p(peak))
+    return labels, dists, found, hops, nbrs, peak

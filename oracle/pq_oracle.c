@@ -458,3 +458,110 @@ ORC_API int orc_single_list_walk(const uint8_t *level0, uint64_t size_per_elem, 
   free(K); free(V); free(X); free(res);
   return 0;
 }
+
+/* NOT the reference's algorithm either: the scalar model of hnsw_walk_flagged (one sorted list of every
+ * candidate with a PASS flag, lowerBound read off the list, capacity `cap`; see hnsw_search.cu).  `filter`
+ * is the internal-id bitmap of orc_hnsw_search or NULL (then deleted nodes do not pass).  found[b] = -1
+ * when the list would outgrow `cap` (the kernel flags the query and the host re-runs the batch on the
+ * bitmap walk); out_peak[b] = the largest list size reached (drives the host's capacity rule).          */
+ORC_API int orc_flagged_walk(const uint8_t *level0, uint64_t size_per_elem, uint64_t offset_data,
+                             uint64_t label_offset, const uint8_t *links, const uint64_t *link_off,
+                             const int32_t *levels, uint64_t size_links_per_elem, int64_t n,
+                             int32_t maxlevel, uint32_t enterpoint, int M, int Ks, int code_bytes,
+                             const float *tables, int64_t B, int k, int ef_, const uint8_t *filter, int cap,
+                             uint64_t *out_labels, float *out_dists, int32_t *found, int64_t *out_hops,
+                             int64_t *out_nbrs, int32_t *out_peak) {
+  graph_t g = {level0, size_per_elem, offset_data, label_offset, links, link_off, levels,
+               size_links_per_elem, n, maxlevel, enterpoint, M, Ks, code_bytes};
+  if (n == 0) { for (int64_t b = 0; b < B; b++) found[b] = 0; return 0; }
+  const int ef = ef_ > k ? ef_ : k;
+  int has_del = 0;
+  for (int64_t i = 0; i < n && !has_del; i++) has_del = g_deleted(&g, (uint32_t)i);
+  const size_t room = (size_t)cap + 65;
+  float *K = (float *)malloc(sizeof(float) * room);
+  uint32_t *V = (uint32_t *)malloc(sizeof(uint32_t) * room);
+  uint8_t *X = (uint8_t *)malloc(room), *P = (uint8_t *)malloc(room);
+  res_t *res = (res_t *)malloc(sizeof(res_t) * room);
+  for (int64_t b = 0; b < B; b++) {
+    const float *t = tables + (size_t)b * M * Ks;
+    int64_t hops = 0, nbrs = 0;
+    uint32_t cur = enterpoint;
+    float curdist = pq_lookup(t, M, Ks, g_code(&g, cur), code_bytes);
+    for (int level = maxlevel; level > 0; level--) {
+      int changed = 1;
+      while (changed) {
+        changed = 0;
+        const uint8_t *ll = g_list(&g, cur, level);
+        unsigned size = g_count(ll);
+        hops++;
+        nbrs += size;
+        for (unsigned i = 0; i < size; i++) {
+          uint32_t cand = g_link(ll, i);
+          float d = pq_lookup(t, M, Ks, g_code(&g, cand), code_bytes);
+          if (d < curdist) { curdist = d; cur = cand; changed = 1; }
+        }
+      }
+    }
+#define PASSES(id) (filter ? (int)((filter[(id) >> 3] >> ((id) & 7)) & 1) : !g_deleted(&g, (id)))
+    int size = 1, peak = 1, aborted = 0;
+    K[0] = curdist; V[0] = cur; X[0] = 1; P[0] = (uint8_t)PASSES(cur);
+    int npass = P[0];
+    float lb = P[0] ? curdist : FLT_MAX;
+    uint32_t node = cur;
+    for (;;) {
+      const uint8_t *ll = g_list(&g, node, 0);
+      unsigned cnt = g_count(ll);
+      hops++;
+      nbrs += cnt;
+      const float lb0 = lb;
+      const int npass0 = npass, size0 = size;
+      int added = 0;
+      for (unsigned j = 0; j < cnt; j++) {
+        uint32_t x = g_link(ll, j);
+        float d = pq_lookup(t, M, Ks, g_code(&g, x), code_bytes);
+        if (!(npass0 < ef || d < lb0)) continue;                 /* :306 / :413 at the hop's start */
+        int pos = 0, dup = 0;
+        while (pos < size && K[pos] <= d) pos++;
+        for (int i = pos - 1; i >= 0 && K[i] == d; i--) if (V[i] == x) { dup = 1; break; }
+        if (dup) continue;
+        if (size0 + ++added > cap) { aborted = 1; break; }
+        memmove(K + pos + 1, K + pos, sizeof(float) * (size_t)(size - pos));
+        memmove(V + pos + 1, V + pos, sizeof(uint32_t) * (size_t)(size - pos));
+        memmove(X + pos + 1, X + pos, (size_t)(size - pos));
+        memmove(P + pos + 1, P + pos, (size_t)(size - pos));
+        K[pos] = d; V[pos] = x; X[pos] = 0; P[pos] = (uint8_t)PASSES(x);
+        size++;
+      }
+      if (aborted) break;
+      if (size > peak) peak = size;
+      if (added) {
+        int total = 0, pef = -1, plast = -1;
+        for (int i = 0; i < size; i++) if (P[i]) { total++; plast = i; if (total == ef && pef < 0) pef = i; }
+        if (total >= ef) { size = pef + 1; npass = ef; lb = K[pef]; }
+        else { npass = total; if (total > 0) lb = K[plast]; }
+      }
+      int nx = -1;
+      for (int i = 0; i < size; i++) if (!X[i]) { nx = i; break; }
+      if (nx < 0) break;
+      if (filter) { if (K[nx] > lb) break; }
+      else if (K[nx] > lb && (npass == ef || !has_del)) break;
+      X[nx] = 1;
+      node = V[nx];
+    }
+#undef PASSES
+    int cnt = 0;
+    if (!aborted)
+      for (int i = 0; i < size && cnt < k; i++) if (P[i]) { res[cnt].d = K[i]; res[cnt].l = g_label(&g, V[i]); cnt++; }
+    qsort(res, (size_t)cnt, sizeof(res_t), res_cmp);
+    for (int i = 0; i < k; i++) {
+      out_dists[(size_t)b * k + i] = i < cnt ? res[i].d : FLT_MAX;
+      out_labels[(size_t)b * k + i] = i < cnt ? res[i].l : UINT64_MAX;
+    }
+    found[b] = aborted ? -1 : cnt;
+    if (out_hops) out_hops[b] = hops;
+    if (out_nbrs) out_nbrs[b] = nbrs;
+    if (out_peak) out_peak[b] = peak;
+  }
+  free(K); free(V); free(X); free(P); free(res);
+  return 0;
+}

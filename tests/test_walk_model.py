@@ -182,3 +182,43 @@ def test_single_list_model_vs_oracle_at_gpu_test_shapes(shape):
         assert (v[clean] == 'exact').all()
         assert np.array_equal(mh[clean], hops[clean]) and np.array_equal(mn[clean], nbrs[clean])
         assert (v[~clean] == 'diff').sum() <= 1
+
+
+# ---- flagged single-list walk (filters / deletions): scalar C model vs the oracle -------------------------
+@pytest.mark.parametrize('mode', ['filter', 'deleted'])
+def test_flagged_model_vs_oracle_on_fixtures(golden, mode):
+    from helpers import tie_aware_rows
+    g = golden.oracle_graph(deleted=(mode == 'deleted'))
+    fl = golden.allow if mode == 'filter' else None
+    t = golden.query_tables_oracle()
+    ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t, golden.k, golden.ef, filter_labels=fl, with_counts=True, with_ties=True)
+    ml, md, mf, mh, mn, peak = O.flagged_walk(g, t, golden.k, golden.ef, filter_labels=fl, cap=512)
+    assert np.array_equal(mf, found)
+    v = np.array(tie_aware_rows(ml, md, ol, od))
+    clean = ties == 0
+    assert (v[clean] == 'exact').all()
+    assert np.array_equal(mh[clean], hops[clean]) and np.array_equal(mn[clean], nbrs[clean])
+    assert (v[~clean] == 'diff').sum() <= (3 if golden.name == 'ties_k16' else 0)
+
+
+def test_flagged_model_capacity_rule_and_overflow_flag():
+    """The host's capacity rule (launch_search: 1.3*ef/s + 48) against the peak list size the walk reaches under
+    random filters, and the overflow flag (found = -1) when the capacity is too small on purpose."""
+    from helpers import tie_aware_rows
+    g, t = _host_built(20000, 64, 8, 256, 21, threads=8)
+    rng = np.random.default_rng(4)
+    labels = g.labels()
+    for ef, s in ((64, 0.9), (64, 0.5), (64, 0.3), (128, 0.5)):
+        allow = labels[rng.random(g.n) < s]
+        need = ef / (len(allow) / g.n) * 1.3 + 48
+        cap = next(c for c in (64, 128, 256, 512) if c >= need and c >= ef)
+        ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t, 10, ef, filter_labels=allow, with_counts=True, with_ties=True)
+        ml, md, mf, mh, mn, peak = O.flagged_walk(g, t, 10, ef, filter_labels=allow, cap=cap)
+        assert (mf == found).all() and peak.max() <= cap          # no query overflows under a random filter
+        v = np.array(tie_aware_rows(ml, md, ol, od))
+        clean = ties == 0
+        assert (v[clean] == 'exact').all() and np.array_equal(mh[clean], hops[clean])
+        assert (v[~clean] == 'diff').sum() <= 1
+    allow = labels[rng.random(g.n) < 0.3]
+    ml, md, mf, mh, mn, peak = O.flagged_walk(g, t, 10, 64, filter_labels=allow, cap=128)   # needs ~ 64/0.3 = 213 entries
+    assert (mf == -1).mean() > 0.9
