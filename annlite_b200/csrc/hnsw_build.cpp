@@ -370,6 +370,11 @@ struct Worker {
         memcpy(snap, list_links(ll), size * sizeof(uint32_t));
       }
       const uint32_t *nb = snap;
+      // every neighbour costs two cache misses (its visited tag, its code row): issue them all up front
+      for (unsigned j = 0; j < size; j++) {
+        __builtin_prefetch(&seen[nb[j]]);
+        __builtin_prefetch(g.code(nb[j]));
+      }
       for (unsigned j = 0; j < size; j++) {
         const uint32_t cid = nb[j];
         if (seen[cid] == tag) continue;
@@ -381,6 +386,11 @@ struct Worker {
           if (top.size() > efc) top.pop();
           if (!top.empty()) lower = top.top().first;
         }
+      }
+      if (!cand.empty()) {  // the node expanded next (unless the loop ends): start pulling its link list
+        const uint8_t *nl = g.list_at(cand.top().second, layer);
+        __builtin_prefetch(nl);
+        __builtin_prefetch(nl + 64);
       }
     }
   }
@@ -455,6 +465,7 @@ struct Worker {
         set_list_count(ll, (unsigned)sz + 1);
       } else {
         // "finding the weakest element": in PQ mode every distance below is dist_to_new(other)
+        for (size_t j = 0; j < sz; j++) __builtin_prefetch(g.code(data[j]));  // select_neighbors scores them all
         const float d_max = dist_to_new(other);
         FarHeap &cands = h_cands;
         cands.clear();
