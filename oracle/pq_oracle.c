@@ -17,6 +17,9 @@
  *         -std=c++14 => ISO mode => -ffp-contract=off, setup.py:108-119,151).
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ *
+ * The last two functions of the file (orc_single_list_walk, orc_flagged_walk) are the exception and
+ * are marked as such: scalar models of the PRODUCT's walks, run beside the restatement by CPU tests.
  */
 #include <float.h>
 #include <math.h>
