@@ -144,7 +144,31 @@ class PQCodec:
 
     @staticmethod
     def load(from_path):
-        return pickle.load(open(from_path, 'rb'))
+        """Reads a codec written by ``dump`` -- this class's or the reference's (an existing AnnLite workspace
+        holds ``annlite.core.codec.pq.PQCodec`` pickles): the reference's class and enum paths are mapped onto
+        this package, the attribute names are the same."""
+        with open(from_path, 'rb') as f:
+            obj = _CompatUnpickler(f).load()
+        if not isinstance(obj, PQCodec):
+            raise TypeError(f'{from_path} does not hold a PQCodec (got {type(obj).__name__})')
+        obj.__dict__.setdefault('device', 0)
+        obj.__dict__['_engine'] = None
+        obj.metric = Metric.coerce(obj.metric)
+        obj._codebooks = np.ascontiguousarray(obj._codebooks, dtype=np.float32)
+        return obj
+
+
+class _CompatUnpickler(pickle.Unpickler):
+    _MAP = {('annlite.core.codec.pq', 'PQCodec'): lambda: PQCodec,
+            ('annlite.enums', 'Metric'): lambda: Metric}
+
+    def find_class(self, module, name):
+        hit = self._MAP.get((module, name))
+        if hit is not None:
+            return hit()
+        if module == 'annlite' or module.startswith('annlite.'):
+            raise pickle.UnpicklingError(f'{module}.{name} has no counterpart in annlite_b200')
+        return super().find_class(module, name)
 
 
 class DistanceTable:

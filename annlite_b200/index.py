@@ -7,6 +7,9 @@ is what CellTable hands out, annlite/storage/table.py:213-257) or any object wit
 (+ optional `.ids`).  `search()` returns `(dists, ids)` arrays; a `filter` is given as the array of
 admissible ids (what CellTable.query would yield, container.py:107-120).
 """
+import datetime
+import hashlib
+import shutil
 from pathlib import Path
 from typing import Optional, Union
 
@@ -43,23 +46,47 @@ class AnnLite:
         self._pq_codec = PQCodec(dim=n_dim, n_subvectors=n_subvectors, n_clusters=n_clusters, metric=self.metric,
                                  device=device)
         if self._pq_codec_path.exists():
-            self._pq_codec = PQCodec.load(self._pq_codec_path)
+            self._pq_codec = PQCodec.load(self._pq_codec_path)     # reads the reference's own pickles too
+            self._pq_codec.device = device
         self._kwargs = dict(initial_size=initial_size, expand_step_size=expand_step_size, device=device, **kwargs)
         self._index = None
         self._n = 0
         if self._pq_codec.is_trained:
             self._make_index()
-            if self._index_path.exists():
+            if self.snapshot_path is not None and (self.snapshot_path / 'cell_0.hnsw').exists():
                 self.restore()
 
-    # ---- paths ------------------------------------------------------------------------------------
+    # ---- workspace layout: the reference's (annlite/index.py:573-640), so that a directory written by either
+    # side opens on the other for the part this package covers (codec + cell_0 graph; the document tables of the
+    # snapshot stay with the reference) --------------------------------------------------------------------------
     @property
-    def _pq_codec_path(self):
-        return self.data_path / 'pq_codec.bin'
+    def params_hash(self):
+        metas = (f'n_dim: {self.n_dim} metric: {self.metric} n_cells: {self.n_cells} '
+                 f'n_components: {None} n_subvectors: {self.n_subvectors}')
+        return hashlib.md5(metas.encode()).hexdigest()
 
     @property
-    def _index_path(self):
-        return self.data_path / 'cell_0.hnsw'
+    def model_path(self):
+        return self.data_path / f'parameters-{self.params_hash}'
+
+    @property
+    def _pq_codec_path(self):
+        return self.model_path / 'pq_codec.params'
+
+    @property
+    def index_hash(self):
+        """The reference stamps a snapshot with its last commit time (index.py:601-616); without the meta table
+        the time of the dump stands in.  Same text form: ISO, '#' separator, seconds."""
+        return datetime.datetime.now(datetime.timezone.utc).replace(tzinfo=None).isoformat('#', 'seconds')
+
+    @property
+    def index_path(self):
+        return self.data_path / f'snapshot-{self.params_hash}' / f'{self.index_hash}-SNAPSHOT'
+
+    @property
+    def snapshot_path(self):
+        found = sorted((self.data_path / f'snapshot-{self.params_hash}').glob('*-SNAPSHOT'), key=lambda x: x.name)
+        return found[-1] if found else None
 
     def _make_index(self):
         self._index = HnswIndex(self.n_dim, metric=self.metric, pq_codec=self._pq_codec, **self._kwargs)
@@ -163,17 +190,33 @@ class AnnLite:
 
     # ---- persistence ------------------------------------------------------------------------------------
     def dump_model(self):
+        """annlite/index.py:679-687."""
+        self.model_path.mkdir(parents=True, exist_ok=True)
         self._pq_codec.dump(self._pq_codec_path)
 
     def dump_index(self):
-        self._index.dump(self._index_path)
+        """annlite/index.py:689-710: a fresh `<time>-SNAPSHOT` directory holding cell_0.hnsw (hnswlib format)."""
+        target = self.index_path
+        if target.exists():
+            shutil.rmtree(target)
+        target.mkdir(parents=True)
+        try:
+            self._index.dump(target / 'cell_0.hnsw')
+        except Exception:
+            shutil.rmtree(target, ignore_errors=True)
+            raise
+        return target
 
     def dump(self):
         self.dump_model()
-        self.dump_index()
+        return self.dump_index()
 
     def restore(self):
-        self._index.load(self._index_path)
+        """annlite/index.py:769-777: the latest snapshot of this parameter set."""
+        snap = self.snapshot_path
+        if snap is None:
+            raise FileNotFoundError(f'no snapshot of parameter set {self.params_hash} under {self.data_path}')
+        self._index.load(snap / 'cell_0.hnsw')
         self._n = self._index.size
 
     def close(self):
