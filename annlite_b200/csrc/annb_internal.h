@@ -71,6 +71,10 @@ struct HostGraph {
   uint64_t label(uint32_t id) const;
   bool deleted(uint32_t id) const { return rec0(id)[2] & 1; }
   int load_file(const char *path, int64_t max_elements_i, size_t code_row_bytes_);
+  // Structural soundness of a graph that came from outside (file, pickle state): every count within its list,
+  // every link an existing node that has the level it is linked on, entry point and level bounds.  The
+  // reference trusts its input; here a bad link would become an out-of-bounds read on the GPU.
+  int validate() const;
   int save_file(const char *path) const;
 };
 

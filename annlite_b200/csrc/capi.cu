@@ -251,10 +251,29 @@ int annb_adc_table(annb_index_t *h, const float *queries, int q_space, int64_t B
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------
+// A code is an index into a Ks-entry table row.  Where the code type can hold more than Ks (Ks < 256 with u8
+// codes, ...) a value from outside -- a caller's array, a file -- is checked once on entry: the kernels and the
+// host builder index the table with it unchecked, as the reference does (space_pq.h:30-35).
+static int check_code_rows(annb_index *h, const uint8_t *rows, int64_t n, size_t stride) {
+  const uint64_t full = h->code_bytes == 1 ? 256ull : (h->code_bytes == 2 ? 65536ull : (1ull << 32));
+  if ((uint64_t)h->Ks >= full) return ANNB_OK;
+  for (int64_t i = 0; i < n; i++) {
+    const uint8_t *r = rows + (size_t)i * stride;
+    for (int m = 0; m < h->M; m++) {
+      uint32_t v = 0;
+      memcpy(&v, r + (size_t)m * h->code_bytes, h->code_bytes);
+      if (v >= (uint32_t)h->Ks)
+        ANNB_FAIL(ANNB_EINVAL, "PQ code %u (row %lld, subvector %d) is not below n_clusters=%d", v, (long long)i, m, h->Ks);
+    }
+  }
+  return ANNB_OK;
+}
+
 int annb_set_codes(annb_index_t *h, const void *codes, int space, int64_t n) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
   if (n < 0 || (n > 0 && !codes)) ANNB_FAIL(ANNB_EINVAL, "null codes");
+  if (space != ANNB_DEVICE) ANNB_TRY(check_code_rows(h, (const uint8_t *)codes, n, (size_t)h->M * h->code_bytes));
   ANNB_CUDA(cudaStreamSynchronize(h->stream));
   if (h->d_codes) {
     ANNB_CUDA(cudaFree(h->d_codes));
@@ -340,6 +359,10 @@ int annb_load_index(annb_index_t *h, const char *path, int64_t max_elements) {
   if (!path) ANNB_FAIL(ANNB_EINVAL, "null path");
   ANNB_TRY(h->g.load_file(path, max_elements, (size_t)h->M * h->code_bytes));
   h->dev_dirty = true;
+  if (int rc = check_code_rows(h, h->g.level0 + h->g.offset_data, h->g.count.load(), h->g.size_per_elem)) {
+    h->g.clear();
+    return rc;
+  }
   return ANNB_OK;
 }
 
@@ -365,6 +388,7 @@ int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_da
   if (g.maxM != max_M) ANNB_FAIL(ANNB_EINVAL, "Invalid value of maxM_ ");
   if (g.maxM0 != max_M0) ANNB_FAIL(ANNB_EINVAL, "Invalid value of maxM0_ ");
   if (g.size_links_per_elem != size_links_per_element) ANNB_FAIL(ANNB_EINVAL, "Invalid value of size_links_per_element_ ");
+  if (cur_element_count < 0 || (cur_element_count > 0 && (!data_level0 || !element_levels))) ANNB_FAIL(ANNB_EINVAL, "bad arguments");
   g.mult = mult;
   g.maxlevel = max_level;
   g.enterpoint = enterpoint_node;
@@ -372,6 +396,8 @@ int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_da
   if (n) memcpy(g.level0, data_level0, n * g.size_per_elem);
   size_t off = 0;
   for (size_t i = 0; i < n; i++) {
+    if (element_levels[i] < 0 || element_levels[i] >= 63 || (element_levels[i] > 0 && !link_lists))
+      ANNB_FAIL(ANNB_EINVAL, "Invalid value of element_levels_[%zu]", i);
     g.levels[i] = element_levels[i];
     if (element_levels[i] > 0) {
       const size_t sz = g.size_links_per_elem * (size_t)element_levels[i];
@@ -383,6 +409,20 @@ int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_da
   }
   g.count = (int64_t)n;
   g.num_deleted = 0;
+  int vrc = g.validate();
+  if (vrc == ANNB_OK) vrc = check_code_rows(h, g.level0 + g.offset_data, (int64_t)n, g.size_per_elem);
+  if (int rc = vrc) {  // leave an empty, initialised graph behind
+    g.count = 0;
+    for (size_t i = 0; i < n; i++) {
+      free(g.upper[i]);
+      g.upper[i] = nullptr;
+      g.levels[i] = 0;
+    }
+    g.maxlevel = -1;
+    g.enterpoint = 0xFFFFFFFFu;
+    h->dev_dirty = true;
+    return rc;
+  }
   g.label_lookup.reserve(n);
   for (size_t i = 0; i < n; i++) {
     g.label_lookup[g.label((uint32_t)i)] = (uint32_t)i;
@@ -507,6 +547,7 @@ int annb_add_items(annb_index_t *h, const float *vectors, const void *codes, con
   const size_t crow = (size_t)h->M * h->code_bytes;
   std::vector<uint8_t> own_codes;
   const uint8_t *hc = (const uint8_t *)codes;
+  if (hc) ANNB_TRY(check_code_rows(h, hc, n, crow));
   if (!hc) {  // PQCodec.encode on the GPU, chunked
     own_codes.resize((size_t)n * crow);
     const int64_t step = 1 << 18;
@@ -557,6 +598,7 @@ int annb_add_items_with_tables(annb_index_t *h, const void *codes, const float *
   if (n < 0 || (n > 0 && (!codes || !tables || !labels))) ANNB_FAIL(ANNB_EINVAL, "null codes/tables/labels");
   if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph first");
   if (n == 0) return ANNB_OK;
+  ANNB_TRY(check_code_rows(h, (const uint8_t *)codes, n, (size_t)h->M * h->code_bytes));
   HostTables t{tables, (size_t)h->M * h->Ks};
   int rc = hnsw_insert_rows(h, (const uint8_t *)codes, labels, n, num_threads, host_tables_next, &t, n);
   h->dev_dirty = true;

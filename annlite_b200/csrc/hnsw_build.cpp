@@ -115,6 +115,38 @@ int HostGraph::save_file(const char *path) const {
   return ANNB_OK;
 }
 
+namespace {
+constexpr uint64_t kMaxListLinks = 2048;  // maxM0 = 2*M <= 2048 (annb_init_graph limits M to 1024)
+constexpr int kMaxLevels = 63;
+}  // namespace
+
+int HostGraph::validate() const {
+  const int64_t n = count.load();
+  if (n < 0 || n > max_elements) ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (element count)");
+  if (n == 0) return ANNB_OK;
+  if (enterpoint >= (uint64_t)n || maxlevel < 0 || maxlevel >= kMaxLevels || levels[enterpoint] < maxlevel)
+    ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (entry point %u, max level %d)", enterpoint, maxlevel);
+  for (int64_t i = 0; i < n; i++) {
+    const int lv = levels[i];
+    if (lv < 0 || lv >= kMaxLevels || lv > maxlevel || (lv > 0 && !upper[i]))
+      ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (level %d of node %lld)", lv, (long long)i);
+    for (int l = 0; l <= lv; l++) {
+      const uint8_t *ll = list_at((uint32_t)i, l);
+      uint16_t c;
+      memcpy(&c, ll, 2);
+      if (c > (l ? maxM : maxM0))
+        ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (%u links on level %d of node %lld)", c, l, (long long)i);
+      for (unsigned j = 0; j < c; j++) {
+        uint32_t t;
+        memcpy(&t, ll + 4 + 4 * j, 4);
+        if (t >= (uint64_t)n || levels[t] < l)
+          ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (link %u on level %d of node %lld)", t, l, (long long)i);
+      }
+    }
+  }
+  return ANNB_OK;
+}
+
 // loadIndex: hnswalg.h:738-846
 int HostGraph::load_file(const char *path, int64_t max_elements_i, size_t code_row_bytes_) {
   FILE *f = fopen(path, "rb");
@@ -135,12 +167,29 @@ int HostGraph::load_file(const char *path, int64_t max_elements_i, size_t code_r
   const uint64_t n = hdr6[2];
   const size_t spe = hdr6[3];
   const size_t expect = (size_t)m3[1] * 4 + 4 + code_row_bytes_ + 8;
+  if (m3[0] < 1 || m3[0] > kMaxListLinks || m3[1] < 1 || m3[1] > kMaxListLinks || m3[2] < 1 || m3[2] > kMaxListLinks) {
+    fclose(f);
+    ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (M=%llu, maxM=%llu, maxM0=%llu)",
+              (unsigned long long)m3[2], (unsigned long long)m3[0], (unsigned long long)m3[1]);
+  }
   if (spe != expect || hdr6[5] != m3[1] * 4 + 4 || hdr6[4] != m3[1] * 4 + 4 + code_row_bytes_) {
     fclose(f);
     ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (element size %zu, expected %zu for this PQ geometry)", spe, expect);
   }
+  // everything that sizes an allocation or a read is checked against the file before anything is allocated
+  const uint64_t kMaxNodes = 0xfffffffeull;  // internal ids are 32-bit, 0xffffffff marks "no entry point"
+  if (n > kMaxNodes || hdr6[1] > kMaxNodes || total < 96 || n > ((uint64_t)total - 96) / (spe + 4) || ml < -1 || ml >= kMaxLevels ||
+      efc < 1 || efc > (1ull << 31) || !std::isfinite(mu) || mu < 0.0 || mu > 64.0) {
+    fclose(f);
+    ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported");
+  }
   int64_t maxel = max_elements_i;
-  if (maxel < (int64_t)n) maxel = (int64_t)hdr6[1];
+  if (maxel < (int64_t)n) maxel = (int64_t)hdr6[1];  // hnswalg.h:766-768
+  if (maxel < (int64_t)n) maxel = (int64_t)n;        // a file whose own limit is below its count: keep what it holds
+  if ((uint64_t)maxel > kMaxNodes) {
+    fclose(f);
+    ANNB_FAIL(ANNB_EINVAL, "max_elements exceeds the 32-bit internal id space");
+  }
   clear();
   M = (int)m3[2];
   maxM = (int)m3[0];
@@ -174,6 +223,11 @@ int HostGraph::load_file(const char *path, int64_t max_elements_i, size_t code_r
       ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported");
     }
     if (sz) {
+      const long here = ftell(f);
+      if (sz % size_links_per_elem != 0 || sz / size_links_per_elem >= (size_t)kMaxLevels || here < 0 || (uint64_t)sz > (uint64_t)(total - here)) {
+        fclose(f);
+        ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported");
+      }
       levels[i] = (int32_t)(sz / size_links_per_elem);
       upper[i] = (uint8_t *)malloc(sz);
       if (!upper[i] || fread(upper[i], 1, sz, f) != sz) {
@@ -189,6 +243,10 @@ int HostGraph::load_file(const char *path, int64_t max_elements_i, size_t code_r
   fclose(f);
   count = (int64_t)n;
   num_deleted = 0;
+  if (int rc = validate()) {
+    count = 0;
+    return rc;
+  }
   level_gen = std::default_random_engine();  // the loading constructor never seeds it (hnswalg.h:23-25)
   label_lookup.reserve(n);
   for (uint64_t i = 0; i < n; i++) {

@@ -153,3 +153,70 @@ def test_no_cpu_fallback_on_host_only_handle(golden):
         e.set_codebook(golden.cb)
     with pytest.raises(L.AnnbError):
         e.adc_table(golden.Q)
+
+
+# ---- hostile inputs: a graph from outside is checked before it can reach the GPU -------------------------
+def _small_graph(tmp_path, Ks=16):
+    import oracle as O
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((600, 16)).astype(np.float32)
+    cb = np.stack([X[rng.choice(600, Ks, replace=False), m * 4:(m + 1) * 4] for m in range(4)]).astype(np.float32)
+    e = Engine(16, 4, Ks, 'euclidean', device=-1)
+    e.init_graph(600, M=8, ef_construction=40)
+    e.add_items_with_tables(O.encode(X, cb), O.adc_table(X, cb), np.arange(600, dtype=np.uint64), num_threads=1)
+    p = str(tmp_path / 'g.hnsw')
+    e.save_index(p)
+    return e, p, open(p, 'rb').read()
+
+
+def test_corrupted_index_files_are_rejected_not_trusted(tmp_path):
+    import struct
+    e, p, good = _small_graph(tmp_path)
+    spe = struct.unpack_from('<Q', good, 24)[0]
+
+    def load(mut):
+        q = str(tmp_path / 'bad.hnsw')
+        open(q, 'wb').write(bytes(mut))
+        Engine(16, 4, 16, 'euclidean', device=-1).load_index(q)
+
+    load(good)                                                   # the untouched file loads
+    cases = {}
+    b = bytearray(good); b[8:16] = struct.pack('<Q', 10); b[16:24] = struct.pack('<Q', 1 << 40); cases['count beyond the file'] = b
+    b = bytearray(good); b[8:16] = struct.pack('<Q', 3); cases['limit below count'] = None      # tolerated: clamped to the count
+    b = bytearray(good); b[52:56] = struct.pack('<I', 100000); cases['entry point out of range'] = b
+    b = bytearray(good); b[48:52] = struct.pack('<i', 40); cases['max level above every node'] = b
+    b = bytearray(good); b[96 + 4:96 + 8] = struct.pack('<I', 0x7fffffff); cases['level-0 link out of range'] = b
+    b = bytearray(good); b[96:98] = struct.pack('<H', 999); cases['level-0 count above maxM0'] = b
+    b = bytearray(good); b[96 + spe - 12] = 200; cases['code not below Ks'] = b                 # Ks=16, u8 codes
+    b = bytearray(good[:len(good) // 2]); cases['truncated'] = b
+    b = bytearray(good); b[80:88] = struct.pack('<d', float('nan')); cases['mult is NaN'] = b
+    for name, mut in cases.items():
+        if mut is None:
+            continue
+        with pytest.raises(L.AnnbError):
+            load(mut)
+
+
+def test_set_graph_checks_the_state_it_is_given(tmp_path):
+    e, p, good = _small_graph(tmp_path)
+    st = e.get_graph()
+    Engine(16, 4, 16, 'euclidean', device=-1).set_graph(st)      # the untouched state is accepted
+    bad = dict(st); l0 = np.array(st['data_level0']).copy().view(np.uint8); l0[4:8] = np.frombuffer(np.uint32(123456).tobytes(), np.uint8); bad['data_level0'] = l0
+    with pytest.raises(L.AnnbError):
+        Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
+    bad = dict(st); bad['enterpoint_node'] = 60000
+    with pytest.raises(L.AnnbError):
+        Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
+    lv = np.array(st['element_levels']).copy(); lv[5] = -3; bad = dict(st); bad['element_levels'] = lv
+    with pytest.raises(L.AnnbError):
+        Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
+
+
+def test_codes_outside_the_codebook_are_refused(tmp_path):
+    import oracle as O
+    e = Engine(16, 4, 16, 'euclidean', device=-1)
+    e.init_graph(10, M=8, ef_construction=40)
+    codes = np.full((3, 4), 16, dtype=np.uint8)                  # valid codes are 0..15
+    with pytest.raises(L.AnnbError, match='not below n_clusters'):
+        e.add_items_with_tables(codes, np.zeros((3, 4, 16), np.float32), np.arange(3, dtype=np.uint64), num_threads=1)
+    assert e.element_count == 0
