@@ -39,8 +39,8 @@ PROTOTYPES = {
     'annb_init_graph': (_int, [_vp, _i64, _int, _int, _u64]),
     'annb_load_index': (_int, [_vp, _cp, _i64]),
     'annb_save_index': (_int, [_vp, _cp]),
-    'annb_set_graph': (_int, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _u64, _i64, _i64, _i32, _u32, _int, _int,
-                              _int, _int, _f64]),
+    'annb_set_graph': (_int, [_vp, _vp, _u64, _u64, _u64, _u64, _vp, _u64, _vp, _i64, _u64, _i64, _i64, _i32, _u32,
+                              _int, _int, _int, _int, _f64]),
     'annb_graph_info': (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_u64), C.POINTER(_u64),
                                C.POINTER(_i32), C.POINTER(_u32), C.POINTER(_int), C.POINTER(_int),
                                C.POINTER(_int), C.POINTER(_int), C.POINTER(_f64)]),

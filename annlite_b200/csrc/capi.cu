@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <limits>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -373,11 +374,16 @@ int annb_save_index(annb_index_t *h, const char *path) {
   return h->g.save_file(path);
 }
 
-int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_data_per_element, uint64_t offset_data,
-                   uint64_t label_offset, const uint8_t *link_lists, const int32_t *element_levels,
-                   uint64_t size_links_per_element, int64_t cur_element_count, int64_t max_elements, int32_t max_level,
-                   uint32_t enterpoint_node, int max_M, int max_M0, int M, int ef_construction, double mult) {
+int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t data_level0_bytes, uint64_t size_data_per_element,
+                   uint64_t offset_data, uint64_t label_offset, const uint8_t *link_lists, uint64_t link_lists_bytes,
+                   const int32_t *element_levels, int64_t n_element_levels, uint64_t size_links_per_element,
+                   int64_t cur_element_count, int64_t max_elements, int32_t max_level, uint32_t enterpoint_node, int max_M,
+                   int max_M0, int M, int ef_construction, double mult) {
   ANNB_ENTER(h);
+  if (cur_element_count < 0 || cur_element_count > 0xfffffffell || n_element_levels < cur_element_count ||
+      (size_data_per_element && data_level0_bytes / size_data_per_element < (uint64_t)cur_element_count) || M <= 0 || M > 1024 ||
+      ef_construction < 1 || !std::isfinite(mult) || mult < 0.0 || mult > 64.0)
+    ANNB_FAIL(ANNB_EINVAL, "graph state is inconsistent with the sizes of its arrays");
   HostGraph &g = h->g;
   const size_t crow = (size_t)h->M * h->code_bytes;
   if (max_elements < cur_element_count) max_elements = cur_element_count;
@@ -401,6 +407,15 @@ int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_da
     g.levels[i] = element_levels[i];
     if (element_levels[i] > 0) {
       const size_t sz = g.size_links_per_elem * (size_t)element_levels[i];
+      if (off + sz > link_lists_bytes) {
+        for (size_t j = 0; j < i; j++) {
+          free(g.upper[j]);
+          g.upper[j] = nullptr;
+          g.levels[j] = 0;
+        }
+        g.levels[i] = 0;
+        ANNB_FAIL(ANNB_EINVAL, "element_levels_ ask for more link-list bytes than link_lists holds");
+      }
       g.upper[i] = (uint8_t *)malloc(sz);
       if (!g.upper[i]) ANNB_FAIL(ANNB_ENOMEM, "Not enough memory: loadIndex failed to allocate linklist");
       memcpy(g.upper[i], link_lists + off, sz);

@@ -123,7 +123,11 @@ constexpr int kMaxLevels = 63;
 int HostGraph::validate() const {
   const int64_t n = count.load();
   if (n < 0 || n > max_elements) ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (element count)");
-  if (n == 0) return ANNB_OK;
+  if (n == 0) {  // the empty graph of hnswalg.h:61-62
+    if (enterpoint != 0xFFFFFFFFu || maxlevel != -1)
+      ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (empty graph with entry point %u, max level %d)", enterpoint, maxlevel);
+    return ANNB_OK;
+  }
   if (enterpoint >= (uint64_t)n || maxlevel < 0 || maxlevel >= kMaxLevels || levels[enterpoint] < maxlevel)
     ANNB_FAIL(ANNB_EIO, "Index seems to be corrupted or unsupported (entry point %u, max level %d)", enterpoint, maxlevel);
   for (int64_t i = 0; i < n; i++) {

@@ -115,8 +115,9 @@ class Engine:
             ll = np.zeros(8, dtype=np.uint8)
         lv = np.ascontiguousarray(np.asarray(st['element_levels'], dtype=np.int32))
         L.check(self._lib.annb_set_graph(
-            self._h, l0.ctypes.data, int(st['size_data_per_element']), int(st['offset_data']), int(st['label_offset']),
-            ll.ctypes.data, lv.ctypes.data, int(st['size_links_per_element']), int(st['cur_element_count']),
+            self._h, l0.ctypes.data, int(l0.nbytes), int(st['size_data_per_element']), int(st['offset_data']),
+            int(st['label_offset']), ll.ctypes.data, int(np.asarray(st['link_lists']).nbytes), lv.ctypes.data, int(lv.size),
+            int(st['size_links_per_element']), int(st['cur_element_count']),
             int(st['max_elements']), int(st['max_level']), int(st['enterpoint_node']) & 0xFFFFFFFF, int(st['max_M']),
             int(st['max_M0']), int(st['M']), int(st['ef_construction']), float(st['mult'])))
 

@@ -132,12 +132,16 @@ ANNB_API int annb_save_index(annb_index_t *h, const char *path);
 
 /* Index.__setstate__ / createFromParams + setAnnData (hnsw_bindings.cpp:691-841): adopt a graph
  * given as the raw arrays of the reference's pickle dict. */
-ANNB_API int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t size_data_per_element,
-                   uint64_t offset_data, uint64_t label_offset, const uint8_t *link_lists,
-                   const int32_t *element_levels, uint64_t size_links_per_element,
+ANNB_API int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t data_level0_bytes,
+                   uint64_t size_data_per_element, uint64_t offset_data, uint64_t label_offset,
+                   const uint8_t *link_lists, uint64_t link_lists_bytes, const int32_t *element_levels,
+                   int64_t n_element_levels, uint64_t size_links_per_element,
                    int64_t cur_element_count, int64_t max_elements, int32_t max_level,
                    uint32_t enterpoint_node, int max_M, int max_M0, int M, int ef_construction,
                    double mult);
+/* The three array extents (bytes of data_level0 / link_lists, entries of element_levels) are what the
+ * caller really holds; the state is rejected (ANNB_EINVAL) if cur_element_count or the levels ask for
+ * more, and then checked structurally like a loaded file. */
 
 /* Index.__getstate__ (hnsw_bindings.cpp:549-671): sizes first, then copy-out. */
 ANNB_API int annb_graph_info(annb_index_t *h, int64_t *cur_element_count, int64_t *max_elements,

@@ -210,6 +210,16 @@ def test_set_graph_checks_the_state_it_is_given(tmp_path):
     lv = np.array(st['element_levels']).copy(); lv[5] = -3; bad = dict(st); bad['element_levels'] = lv
     with pytest.raises(L.AnnbError):
         Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
+    # arrays shorter than the counts claim: the extents travel with the pointers (include/annb.h)
+    bad = dict(st); bad['link_lists'] = np.array(st['link_lists'])[:-8]
+    with pytest.raises(L.AnnbError, match='link-list bytes'):
+        Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
+    bad = dict(st); bad['data_level0'] = np.array(st['data_level0'])[:-80]
+    with pytest.raises(L.AnnbError, match='inconsistent'):
+        Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
+    bad = dict(st); bad['cur_element_count'] = 0            # an "empty" graph that still names an entry point
+    with pytest.raises(L.AnnbError):
+        Engine(16, 4, 16, 'euclidean', device=-1).set_graph(bad)
 
 
 def test_codes_outside_the_codebook_are_refused(tmp_path):
