@@ -14,6 +14,30 @@ from .engine import Engine
 _NO_TABLES = 'Row index exceeds or batch distance table uninitialized, most likely an internal bug!'
 
 
+def default_threads():
+    """Insertion threads when the caller names none.  The reference takes hardware_concurrency()
+    (hnsw_bindings.cpp:104); here, like ``hnsw_default_threads()`` in the library, the CPUs this process may really
+    use (affinity mask, cgroup quota), capped at 32 -- the measured optimum on the B200 hosts."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = -1, -1
+        if os.path.exists('/sys/fs/cgroup/cpu.max'):
+            q, p = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+            quota, period = (-1 if q == 'max' else int(q)), int(p)
+        elif os.path.exists('/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+            quota = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            period = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+        if quota > 0 and period > 0:
+            n = min(n, max(1, -(-quota // period)))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))
+
+
 class Index:
     ser_version = 1
 
@@ -27,7 +51,7 @@ class Index:
         self.pq_enable = False
         self.pq_codec = None
         self.default_ef = 10
-        self.num_threads = os.cpu_count() or 1
+        self.num_threads = default_threads()
         self.index_inited = False
         self.ep_added = True
         self._init_args = None
