@@ -112,6 +112,21 @@ class AnnLite:
         if auto_save:
             self.dump_model()
 
+    def partial_train(self, x: 'np.ndarray', auto_save: bool = True, force_train: bool = False):
+        """annlite/index.py:235-272: feed one batch to the PQ codec's mini-batch k-means; the codec becomes trained
+        once ``build_codebook()`` is called on it (annlite/core/codec/pq.py:145-156), exactly as in the reference."""
+        self._sanity_check(x)
+        if self.is_trained and not force_train:
+            return
+        self._pq_codec.partial_fit(np.ascontiguousarray(x, dtype=np.float32))
+        if auto_save:
+            self.dump_model()
+
+    def build_codebook(self):
+        """Finish a ``partial_train`` sequence and create the graph backend for the trained codec."""
+        self._pq_codec.build_codebook()
+        self._make_index()
+
     def set_codebook(self, codebooks):
         self._pq_codec.set_codebook(codebooks)
         self._make_index()
@@ -187,6 +202,46 @@ class AnnLite:
 
     def delete(self, ids, **kwargs):
         self._index.delete([int(i) for i in ids])
+
+    def clear(self):
+        """annlite/index.py:539-545 for the part kept here: an empty graph of the initial capacity."""
+        if self._index is not None:
+            self._index.reset()
+        self._n = 0
+
+    def encode(self, x: 'np.ndarray'):
+        """annlite/index.py:551-560.  The reference PQ-encodes only when a VQ codec exists (``if self._vq_codec``),
+        i.e. never with one cell: the vectors come back as they are.  Kept as it is; ``self._pq_codec.encode`` is the
+        GPU encoder."""
+        self._sanity_check(x)
+        return x
+
+    def decode(self, x: 'np.ndarray'):
+        """annlite/index.py:562-572: PQ codes (n, n_subvectors) -> reconstructed vectors."""
+        assert len(x.shape) == 2
+        assert x.shape[1] == self.n_subvectors
+        return self._pq_codec.decode(x)
+
+    def vec_index(self, cell_id: int = 0):
+        """annlite/container.py: the per-cell vector index (one cell here)."""
+        if cell_id != 0:
+            raise IndexError('annlite_b200.AnnLite has one cell')
+        return self._index
+
+    @property
+    def cell_indexes(self):
+        return [self._index]
+
+    @property
+    def total_docs(self):
+        return self.index_size
+
+    def backup(self, target_name: Optional[str] = None, token: Optional[str] = None):
+        """annlite/index.py:652-664: without a target this is a local ``dump()``; the remote (Hubble) store is out
+        of scope."""
+        if target_name:
+            raise NotImplementedError('remote backup (Hubble) is out of scope: SURVEY.md section 2')
+        return self.dump()
 
     # ---- persistence ------------------------------------------------------------------------------------
     def dump_model(self):

@@ -79,3 +79,22 @@ def test_dump_writes_the_same_layout_and_restore_reads_it_back(tmp_path, fake):
     assert fake.made[0].loaded == str(snap / 'cell_0.hnsw')
     b = mod.AnnLite(16, metric='cosine', n_subvectors=4, n_clusters=16, data_path=tmp_path)   # reopen: restores by itself
     assert b.index_size == 123
+
+
+def test_small_surface_calls_that_need_no_gpu(tmp_path, fake):
+    import numpy as np
+    h = ref_hash(16, 'COSINE', 4)
+    (tmp_path / f'parameters-{h}').mkdir()
+    shutil.copy(os.path.join(G, 'ref_codec_cosine.pkl'), tmp_path / f'parameters-{h}' / 'pq_codec.params')
+    a = mod.AnnLite(16, metric='cosine', n_subvectors=4, n_clusters=16, data_path=tmp_path)
+    x = np.random.default_rng(0).standard_normal((5, 16)).astype(np.float32)
+    assert a.encode(x) is x                                   # the reference's one-cell quirk (index.py:557)
+    codes = np.random.default_rng(1).integers(0, 16, (5, 4)).astype(np.uint8)
+    rec = a.decode(codes)
+    assert rec.shape == (5, 16) and np.array_equal(rec[:, :4], a._pq_codec.codebooks[0][codes[:, 0]])
+    assert a.vec_index(0) is a.cell_indexes[0] and a.total_docs == a.index_size
+    with pytest.raises(IndexError):
+        a.vec_index(1)
+    with pytest.raises(NotImplementedError):
+        a.backup('somewhere', token='t')
+    assert a.backup().name.endswith('-SNAPSHOT')
