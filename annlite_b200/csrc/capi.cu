@@ -349,7 +349,8 @@ int annb_scan_topk(annb_index_t *h, const float *queries, const float *tables, i
 // ---- graph ------------------------------------------------------------------------------------
 int annb_init_graph(annb_index_t *h, int64_t max_elements, int M, int ef_construction, uint64_t random_seed) {
   ANNB_ENTER(h);
-  if (max_elements < 0 || M <= 0 || M > 1024) ANNB_FAIL(ANNB_EINVAL, "bad max_elements / M");
+  // M = 1 makes the level multiplier 1/ln(M) infinite (hnswalg.h:47) and the reference's level draw undefined
+  if (max_elements < 0 || M < 2 || M > 1024) ANNB_FAIL(ANNB_EINVAL, "bad max_elements / M (2 <= M <= 1024)");
   ANNB_TRY(h->g.init(max_elements, M, ef_construction, random_seed, (size_t)h->M * h->code_bytes));
   h->dev_dirty = true;
   return ANNB_OK;
@@ -381,7 +382,7 @@ int annb_set_graph(annb_index_t *h, const uint8_t *data_level0, uint64_t data_le
                    int max_M0, int M, int ef_construction, double mult) {
   ANNB_ENTER(h);
   if (cur_element_count < 0 || cur_element_count > 0xfffffffell || n_element_levels < cur_element_count ||
-      (size_data_per_element && data_level0_bytes / size_data_per_element < (uint64_t)cur_element_count) || M <= 0 || M > 1024 ||
+      (size_data_per_element && data_level0_bytes / size_data_per_element < (uint64_t)cur_element_count) || M < 2 || M > 1024 ||
       ef_construction < 1 || !std::isfinite(mult) || mult < 0.0 || mult > 64.0)
     ANNB_FAIL(ANNB_EINVAL, "graph state is inconsistent with the sizes of its arrays");
   HostGraph &g = h->g;
