@@ -111,7 +111,14 @@ struct GraphDev {
 };
 
 struct SearchParams {
-  const float *tables;  // (B, M, Ks)
+  const float *tables;  // (B, M, Ks), or nullptr when the walk builds its tables itself (fused K1, hnsw_walk4)
+  const float *queries; // (B, D) device, already normalised where the metric asks for it; nullptr = use `tables`
+  const float *cbt;     // transposed codebook [m][j/V][c][V] for the fused build
+  int cb_vec;           // V: 4 or 2 floats per codeword load
+  int ds;               // subvector length
+  int is_ip;            // IP / COSINE table form: bias - <cb, q>
+  float bias;           // fp32(1/Ks), or 0 for the raw pq_bind form
+  float *dump_tables;   // debug: (B, M, Ks) device buffer that receives the tables the walk used, or nullptr
   int64_t B;
   int k, ef;
   const uint32_t *filter;  // bitmap by internal id, or nullptr
@@ -145,6 +152,8 @@ struct annb_index {
   std::mutex mu;
 
   float *d_codebook = nullptr;
+  float *d_codebook_t = nullptr;  // transposed copy [m][j/V][c][V] read by the fused table build (hnsw_walk4)
+  int cb_vec = 0;                 // V = 4 (ds % 4 == 0), 2 (ds even) or 0 (no fused build)
   std::vector<float> h_codebook;
 
   // flat code matrix for K2
@@ -188,6 +197,9 @@ struct annb_index {
   int64_t opt_flagged_epl = 0;     // force the flagged walk's list size (entries/32): testing the overflow fallback
   int64_t opt_chunks = 0;          // host-buffer search pipeline depth: 0 = auto, 1 = off
   int64_t opt_ip_raw = 0;          // K1 IP form without the 1/Ks bias: T = 0 - ip (pq_bind compatibility)
+  int64_t opt_walk_kernel = 0;     // plain search: 0 = hnsw_walk4 with fused K1 (default), 1 = round-1 kernels (K1 +
+                                   // hnsw_walk_fast), 2 = hnsw_walk4 over materialised tables (K1 + TMA staging)
+  int64_t opt_dump_tables = 0;     // device pointer: searches copy the tables they used there (debug / parity tests)
 };
 
 int annb_scratch(annb_index *h, int slot, size_t bytes, void **out);
@@ -203,6 +215,10 @@ int launch_pack_rec0(annb_index *h, const uint8_t *d_level0_raw, int64_t n);
 // mode: 0 = fast walk (no filter, no deletions), 1 = filtered/deleted walk, kernel chosen automatically
 // (flagged single-list walk when its list fits, else the bitmap walk), 2 = bitmap walk
 int launch_search(annb_index *h, const SearchParams &p, int mode);
+// hnsw_walk4 (walk_fused.cu): the plain search with the table built inside the walk; returns 1 = not applicable
+bool walk4_applicable(const annb_index *h);
+bool walk4_can_fuse(const annb_index *h);
+int launch_walk4(annb_index *h, const SearchParams &p);
 int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k,
                       uint64_t *labels_out, float *dists_out);
 int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t n_filter, uint32_t *d_by_label,

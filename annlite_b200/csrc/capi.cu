@@ -168,6 +168,7 @@ int annb_destroy(annb_index_t *h) {
   for (auto &p : h->h_pinned)
     if (p) cudaFreeHost(p);
   if (h->d_codebook) cudaFree(h->d_codebook);
+  if (h->d_codebook_t) cudaFree(h->d_codebook_t);
   if (h->d_codes) cudaFree(h->d_codes);
   if (h->d_rec0) cudaFree(h->d_rec0);
   if (h->d_up) cudaFree(h->d_up);
@@ -195,6 +196,20 @@ int annb_set_codebook(annb_index_t *h, const float *codebook, int space) {
   else
     memcpy(h->h_codebook.data(), codebook, bytes);
   ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  // transposed copy for the table build inside the walk (hnsw_walk4): [m][j/V][c][V], V floats per load, so
+  // that the 32 lanes of a warp (32 consecutive codewords c) read one contiguous 32*V*4-byte run
+  h->cb_vec = (h->ds % 4 == 0) ? 4 : (h->ds % 2 == 0 ? 2 : 0);
+  if (h->cb_vec) {
+    const int V = h->cb_vec, nv = h->ds / V;
+    std::vector<float> t(h->h_codebook.size());
+    for (int m = 0; m < h->M; m++)
+      for (int c = 0; c < h->Ks; c++)
+        for (int j = 0; j < h->ds; j++)
+          t[(((size_t)m * nv + j / V) * h->Ks + c) * V + j % V] = h->h_codebook[((size_t)m * h->Ks + c) * h->ds + j];
+    if (!h->d_codebook_t) ANNB_CUDA(cudaMalloc(&h->d_codebook_t, bytes));
+    ANNB_CUDA(cudaMemcpyAsync(h->d_codebook_t, t.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  }
   return ANNB_OK;
 }
 
@@ -216,23 +231,43 @@ int annb_sync(annb_index_t *h) {
 
 // ---- K1 ---------------------------------------------------------------------------------------
 // queries (host/device) -> device tables; `d_tables_out` receives the device pointer used.
-static int build_tables(annb_index *h, const float *queries, int q_space, int64_t B, int normalize, float *d_tables) {
+// queries (host/device) -> device queries, normalised `normalize` times (never the caller's own buffer)
+static int stage_queries(annb_index *h, const float *queries, int q_space, int64_t B, int normalize, int slot, const float **dq_out) {
   if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
   const size_t qbytes = (size_t)B * h->dim * sizeof(float);
   const float *dq;
   if (normalize > 0 && q_space == ANNB_DEVICE) {  // never modify the caller's buffer
     void *d;
-    ANNB_TRY(annb_scratch(h, S_QUERIES, qbytes, &d));
+    ANNB_TRY(annb_scratch(h, slot, qbytes, &d));
     ANNB_CUDA(cudaMemcpyAsync(d, queries, qbytes, cudaMemcpyDeviceToDevice, h->stream));
     dq = (const float *)d;
   } else {
-    ANNB_TRY(stage_in(h, queries, q_space, qbytes, S_QUERIES, (const void **)&dq));
+    ANNB_TRY(stage_in(h, queries, q_space, qbytes, slot, (const void **)&dq));
   }
-  if (h->opt_timing) cudaEventRecord(h->ev[0], h->stream);
   for (int r = 0; r < normalize; r++) ANNB_TRY(launch_l2_normalize(h, const_cast<float *>(dq), B, h->dim));
+  *dq_out = dq;
+  return ANNB_OK;
+}
+
+// queries (host/device) -> device tables (K1 as a kernel of its own: the literal pq_bind calls, K2, insertion)
+static int build_tables(annb_index *h, const float *queries, int q_space, int64_t B, int normalize, float *d_tables) {
+  const float *dq;
+  if (h->opt_timing) cudaEventRecord(h->ev[0], h->stream);
+  ANNB_TRY(stage_queries(h, queries, q_space, B, normalize, S_QUERIES, &dq));
   ANNB_TRY(launch_adc_table(h, dq, B, d_tables));
   if (h->opt_timing) cudaEventRecord(h->ev[1], h->stream);
   return ANNB_OK;
+}
+
+// fill the fused-build fields of a SearchParams (hnsw_walk4 builds each query's table in shared memory)
+static void fuse_params(annb_index *h, SearchParams &p, const float *d_queries) {
+  p.tables = nullptr;
+  p.queries = d_queries;
+  p.cbt = h->d_codebook_t;
+  p.cb_vec = h->cb_vec;
+  p.ds = h->ds;
+  p.is_ip = h->metric != ANNB_METRIC_L2;
+  p.bias = h->opt_ip_raw ? 0.f : (float)(1.0 / (double)h->Ks);
 }
 
 int annb_adc_table(annb_index_t *h, const float *queries, int q_space, int64_t B, int normalize, float *out, int out_space) {
@@ -859,11 +894,12 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
     if (nch > 8) nch = 8;
     if (queries && in_space != ANNB_DEVICE && host_out && plain && nch > 1 && B >= 2 * nch) {
       const size_t TS = (size_t)h->M * h->Ks;
-      float *dq, *dtab;
+      const bool fuse = walk4_can_fuse(h);  // the walk builds its own tables: no (B,M,Ks) buffer at all
+      float *dq, *dtab = nullptr;
       unsigned int *counters;
       int32_t *hfound;
       ANNB_TRY(annb_scratch(h, S_QUERIES, (size_t)B * h->dim * sizeof(float), (void **)&dq));
-      ANNB_TRY(annb_scratch(h, S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
+      if (!fuse) ANNB_TRY(annb_scratch(h, S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
       ANNB_TRY(annb_scratch(h, S_COUNTER, 256 * 9, (void **)&counters));
       ANNB_TRY(annb_pinned(h, 2, (size_t)B * 4, (void **)&hfound));
       if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
@@ -880,11 +916,13 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
           break;
         }
         for (int r = 0; r < normalize && rc == ANNB_OK; r++) rc = launch_l2_normalize(h, dq + b0 * h->dim, nb, h->dim);
-        if (rc == ANNB_OK) rc = launch_adc_table(h, dq + b0 * h->dim, nb, dtab + b0 * TS);
+        if (rc == ANNB_OK && !fuse) rc = launch_adc_table(h, dq + b0 * h->dim, nb, dtab + b0 * TS);
         if (rc != ANNB_OK) break;
         SearchParams p;
         memset(&p, 0, sizeof(p));
-        p.tables = dtab + b0 * TS;
+        if (fuse) fuse_params(h, p, dq + b0 * h->dim);
+        else p.tables = dtab + b0 * TS;
+        if (h->opt_dump_tables) p.dump_tables = reinterpret_cast<float *>(h->opt_dump_tables) + b0 * TS;
         p.B = nb;
         p.k = k;
         p.ef = ef_eff;
@@ -916,11 +954,14 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
       return ANNB_OK;
     }
   }
-  // tables
+  // tables: handed in (the literal dtables argument), built inside the walk (plain search, hnsw_walk4), or by K1
   const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
-  const float *dt;
+  const float *dt = nullptr, *dq_fused = nullptr;
+  const bool plain_search = !filter_labels && h->g.num_deleted == 0 && !h->opt_force_general;
   if (tables) {
     ANNB_TRY(stage_in(h, tables, in_space, tbytes, S_TABLES, (const void **)&dt));
+  } else if (plain_search && walk4_can_fuse(h)) {
+    ANNB_TRY(stage_queries(h, queries, in_space, B, normalize, S_QUERIES, &dq_fused));
   } else {
     float *t;
     ANNB_TRY(annb_scratch(h, S_TABLES, tbytes, (void **)&t));
@@ -961,7 +1002,9 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   }
   SearchParams p;
   memset(&p, 0, sizeof(p));
-  p.tables = dt;
+  if (dq_fused) fuse_params(h, p, dq_fused);
+  else p.tables = dt;
+  if (h->opt_dump_tables) p.dump_tables = reinterpret_cast<float *>(h->opt_dump_tables);
   p.B = B;
   p.k = k;
   p.ef = ef_eff;
@@ -1101,13 +1144,14 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
   ANNB_TRY(lane_wait(h, lane));  // a lane holds one batch at a time
   const bool host_in = in_space != ANNB_DEVICE, host_out = out_space != ANNB_DEVICE;
   const size_t TS = (size_t)h->M * h->Ks;
-  float *dq = nullptr, *dtab, *dd = dists_out;
+  const bool fuse = walk4_can_fuse(h);
+  float *dq = nullptr, *dtab = nullptr, *dd = dists_out;
   uint64_t *dl = labels_out;
   int32_t *dfound;
   unsigned int *counters;
   // all scratch first: a (re)allocation synchronises both lanes, which is only safe before enqueuing
   if (host_in || normalize > 0) ANNB_TRY(annb_scratch(h, lane ? S_L1_QUERIES : S_QUERIES, (size_t)B * h->dim * sizeof(float), (void **)&dq));
-  ANNB_TRY(annb_scratch(h, lane ? S_L1_TABLES : S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
+  if (!fuse) ANNB_TRY(annb_scratch(h, lane ? S_L1_TABLES : S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
   if (host_out) {
     ANNB_TRY(annb_scratch(h, lane ? S_L1_OUT_L : S_OUT_L, (size_t)B * k * 8, (void **)&dl));
     ANNB_TRY(annb_scratch(h, lane ? S_L1_OUT_D : S_OUT_D, (size_t)B * k * 4, (void **)&dd));
@@ -1128,11 +1172,12 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
     src = dq;
   }
   for (int r = 0; r < normalize && rc == ANNB_OK; r++) rc = launch_l2_normalize(h, dq, B, h->dim);
-  if (rc == ANNB_OK) rc = launch_adc_table(h, src, B, dtab);
+  if (rc == ANNB_OK && !fuse) rc = launch_adc_table(h, src, B, dtab);
   if (rc == ANNB_OK) {
     SearchParams p;
     memset(&p, 0, sizeof(p));
-    p.tables = dtab;
+    if (fuse) fuse_params(h, p, src);
+    else p.tables = dtab;
     p.B = B;
     p.k = k;
     p.ef = ef_eff;
@@ -1213,6 +1258,8 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "ip_raw")) h->opt_ip_raw = value;
   else if (!strcmp(name, "chunks")) h->opt_chunks = value;
   else if (!strcmp(name, "flagged_epl")) h->opt_flagged_epl = value;
+  else if (!strcmp(name, "walk_kernel")) h->opt_walk_kernel = value;
+  else if (!strcmp(name, "dump_tables")) h->opt_dump_tables = value;
   else if (!strcmp(name, "reset_counters")) h->flagged_fallbacks = 0;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;

@@ -35,6 +35,7 @@
 #include <algorithm>
 
 #include "annb_internal.h"
+#include "tma_utils.cuh"
 #include "warp_list.cuh"
 
 namespace {
@@ -101,37 +102,6 @@ __device__ __forceinline__ float score(const float *T, const uint8_t *code_ptr, 
   } else {
     return pq_lookup_mem<CB>(T, code_ptr, M, Ks);
   }
-}
-
-// ---- TMA bulk copy (cp.async.bulk -> SASS UBLKCP) + mbarrier: the 8 KB per-query table is staged
-// global -> shared by ONE instruction issued by one lane; completion is signalled on a per-warp
-// mbarrier by transaction bytes.  Needs 16-byte aligned source/destination/size.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
 }
 
 __device__ __forceinline__ void load_table(float *dst, const float *__restrict__ src, int TS, int lane) {
@@ -1441,6 +1411,11 @@ int launch_search(annb_index *h, const SearchParams &p, int mode) {
     if (rc != 1) return rc;  // launched (or failed for real); 1 = not applicable -> bitmap walk
   }
   const bool general = mode != 0;
+  if (!general && walk4_applicable(h)) {  // the plain search: K1 fused into the walk (walk_fused.cu)
+    const int rc = launch_walk4(h, p);
+    if (rc != 1) return rc;
+  }
+  if (!p.tables) ANNB_FAIL(ANNB_ESTATE, "internal: no tables for the walk");
   const int epl = (p.ef + 31) / 32;
   if (epl <= 2) return dispatch_code<2>(h, p, general);
   if (epl <= 4) return dispatch_code<4>(h, p, general);

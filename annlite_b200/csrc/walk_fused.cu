@@ -1,0 +1,545 @@
+// walk_fused.cu -- K1+K3 in one kernel: the warp that walks a query first builds that query's ADC table
+// straight into its own shared-memory slot, then runs the HNSW walk over PQ codes out of registers.
+//
+// Reference semantics (unchanged from hnsw_search.cu, where the equivalence argument lives):
+//   table : batch_precompute_adc_table[_ip]  bindings/pq_bindings.pyx:149-274 (+ pq.py:316-322 epilogue)
+//           T[m][c] = sum_j (cb[m][c][j] - q[m*ds+j])^2, j sequential, sub / mul / add rounded separately
+//   walk  : searchKnn  include/hnswlib/hnswalg.h:1237-1295 = greedy descent (:1248-1274) +
+//           searchBaseLayerST (:243-329) with PQLookup (include/hnswlib/space_pq.h:16-37)
+//
+// What is different from hnsw_walk_fast (round 1), and why -- that kernel was issue-bound at ~305 warp
+// instructions per hop:
+//   * compile-time M and Ks = 256, u8 codes: a table lookup is byte-extract + LDS with an immediate
+//     row offset + FADD; no run-time m*Ks+code / node*rec_bytes integer chains.
+//   * the ef-bounded result list lives ONLY in registers, blocked (lane l holds positions l*EPL..),
+//     keys as order-preserving u32 images of the fp32 distances so that warp minima are one REDUX.
+//     No shared-memory mirror, no binary search, no rank loops, no __syncwarp in the hop.
+//   * candidates of a hop are consumed smallest-first: the first one that is not already listed is, if
+//     it beats the nearest unexpanded list entry, exactly the next node to expand -- so the next record
+//     is requested at that moment (exact, never a wrong guess) and its DRAM round trip overlaps the
+//     insertions.  Consuming in ascending order also lets lowerBound fall as fast as it can: the loop
+//     stops at the first candidate that no longer beats it (the hop-start admission test of the
+//     single-list walk admits a superset whose tail falls off the list; the final list is identical).
+//   * one insertion = two shuffles (carry from the lane below) + per-slot compare/select; equal keys
+//     keep arrival order (new after old, lower lane first), the tie rule of the single-list model.
+//   * shared memory per query = the table and nothing else: 28 queries per SM at M=8 (was 25).
+//   * K1 fused: the table never exists in HBM.  The codebook is read from L2 through a transposed copy
+//     ([m][j/V][c][V], V = 4 or 2 floats) so that a warp's codeword loads are fully coalesced.
+//     The literal `tables=` call form (the reference's dtables argument) is served by the same kernel:
+//     the table is then staged by one TMA bulk copy (cp.async.bulk + mbarrier) per query.
+//
+// Results, hop and neighbour counters are those of hnsw_walk_fast and of oracle.single_list_walk on
+// every input (same list after every hop, same next node); differences from the reference itself are
+// confined to exact fp32 ties, as before.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "annb_internal.h"
+#include "tma_utils.cuh"
+
+#define FULL_MASK 0xffffffffu
+
+namespace {
+
+constexpr uint32_t EMPTY_LINK = 0xffffffffu;
+constexpr uint32_t EXP_BIT = 0x80000000u;   // list value: node already expanded (empty slots carry it too)
+constexpr uint32_t IDM = 0x7fffffffu;
+constexpr uint32_t KEY_MAX = 0xffffffffu;   // above the image of every finite distance and of +inf
+constexpr int W4_SMEM_OPTIN = 232448;       // 227 KB: the largest dynamic shared-memory size of one CTA
+
+// order-preserving map fp32 -> u32 (a < b  <=>  f2u(a) < f2u(b) for non-NaN, no -0.0: the ADC sum starts
+// at +0.f and x + (-0) never yields -0)
+__device__ __forceinline__ uint32_t f2u(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float u2f(uint32_t u) {
+  return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u));
+}
+
+constexpr int w4_max_warps(int M, int EPL) {
+  const int by_smem = W4_SMEM_OPTIN / (M * 1024 + 8);
+  const int by_regs = EPL <= 4 ? 28 : (EPL == 8 ? 20 : 14);
+  return by_smem < by_regs ? by_smem : by_regs;
+}
+
+// ---- one level-0 record in registers: lane j holds link j and the M code bytes of neighbour j ----
+template <int M>
+struct Rec {
+  uint32_t link;
+  uint32_t cw[M / 4];
+};
+
+template <int M>
+__device__ __forceinline__ void load_codes(uint32_t (&cw)[M / 4], const uint8_t *p) {
+  if (M == 4) {
+    cw[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+  } else if (M == 8) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    cw[0] = t.x;
+    cw[1] = t.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < M / 16; i++) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+      cw[4 * i + 0] = t.x;
+      cw[4 * i + 1] = t.y;
+      cw[4 * i + 2] = t.z;
+      cw[4 * i + 3] = t.w;
+    }
+  }
+}
+
+// PQLookup (space_pq.h:30-35): strictly sequential fp32 sum over the M subquantisers, from 0.f
+template <int M>
+__device__ __forceinline__ float pq_score(const float *T, const uint32_t (&cw)[M / 4]) {
+  float r = 0.f;
+#pragma unroll
+  for (int m = 0; m < M; m++) {
+    const uint32_t code = (cw[m >> 2] >> (8 * (m & 3))) & 0xffu;
+    r = __fadd_rn(r, T[m * 256 + code]);
+  }
+  return r;
+}
+
+// ---- the list: EPL entries per lane, position p = lane*EPL + e, ascending keys, dense from 0 ----
+template <int EPL>
+__device__ __forceinline__ void list_insert(uint32_t (&K)[EPL], uint32_t (&V)[EPL], uint32_t d, uint32_t nv, bool lane0) {
+  uint32_t pk = __shfl_up_sync(FULL_MASK, K[EPL - 1], 1);
+  const uint32_t pv = __shfl_up_sync(FULL_MASK, V[EPL - 1], 1);
+  if (lane0) pk = 0u;  // nothing below position 0: "the entry below stays"
+  // Slot e keeps its entry while key <= d (the new one lands after its equals); otherwise it takes the new
+  // entry if the slot below keeps its own, else the entry of the slot below.  One predicated select per
+  // register, highest slot first so that every source is still the old value.
+#pragma unroll
+  for (int e = EPL - 1; e >= 0; e--) {
+    const uint32_t prk = e > 0 ? K[e - 1] : pk;
+    const uint32_t prv = e > 0 ? V[e - 1] : pv;
+    asm("{\n"
+        ".reg .pred stay, here;\n"
+        "setp.le.u32 stay, %0, %2;\n"
+        "setp.le.u32 here, %3, %2;\n"
+        "@!stay selp.u32 %0, %2, %3, here;\n"
+        "@!stay selp.u32 %1, %4, %5, here;\n"
+        "}\n"
+        : "+r"(K[e]), "+r"(V[e])
+        : "r"(d), "r"(prk), "r"(nv), "r"(prv));
+  }
+}
+
+template <int EPL>
+__device__ __forceinline__ uint32_t list_key_at(const uint32_t (&K)[EPL], int lane_of, int slot_of) {
+  uint32_t sel = K[0];
+#pragma unroll
+  for (int e = 1; e < EPL; e++)
+    if (slot_of == e) sel = K[e];
+  return __shfl_sync(FULL_MASK, sel, lane_of);
+}
+
+// sequential-j accumulation over one vector of coordinates; every sub / mul / add rounded on its own (no FMA)
+__device__ __forceinline__ float acc_l2(float a, const float2 w, const float2 x) {
+  float t = __fsub_rn(w.x, x.x);
+  a = __fadd_rn(a, __fmul_rn(t, t));
+  t = __fsub_rn(w.y, x.y);
+  return __fadd_rn(a, __fmul_rn(t, t));
+}
+__device__ __forceinline__ float acc_l2(float a, const float4 w, const float4 x) {
+  a = acc_l2(a, make_float2(w.x, w.y), make_float2(x.x, x.y));
+  return acc_l2(a, make_float2(w.z, w.w), make_float2(x.z, x.w));
+}
+__device__ __forceinline__ float acc_ip(float a, const float2 w, const float2 x) {
+  a = __fadd_rn(a, __fmul_rn(w.x, x.x));
+  return __fadd_rn(a, __fmul_rn(w.y, x.y));
+}
+__device__ __forceinline__ float acc_ip(float a, const float4 w, const float4 x) {
+  a = acc_ip(a, make_float2(w.x, w.y), make_float2(x.x, x.y));
+  return acc_ip(a, make_float2(w.z, w.w), make_float2(x.z, x.w));
+}
+
+// ---- K1 inside the walk: build this query's table into T (shared) ----------------------------------
+// cbt is the transposed codebook [m][j/V][c][V]; the query is staged in the tail rows of T itself (they are
+// overwritten last, after their part of the query has been consumed; the host checks that this holds).
+template <int M, int V>
+__device__ __forceinline__ void build_table(float *T, const float *__restrict__ qg, const float *__restrict__ cbt, int ds,
+                                            int is_ip, float bias, int lane) {
+  typedef typename std::conditional<V == 4, float4, float2>::type vec_t;
+  const int D = M * ds;
+  const int R = (D + 255) >> 8;
+  float *stage = T + (M - R) * 256;
+  for (int i = lane; i < D; i += 32) stage[i] = __ldg(qg + i);
+  __syncwarp();
+  const int nv = ds / V;
+  const vec_t *cb = reinterpret_cast<const vec_t *>(cbt);
+  for (int m = 0; m < M; m++) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    const vec_t *xq = reinterpret_cast<const vec_t *>(stage + m * ds);
+    const vec_t *cm = cb + (size_t)m * nv * 256 + lane;
+    if (!is_ip) {
+      for (int jv = 0; jv < nv; jv++) {
+        const vec_t x = xq[jv];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = acc_l2(acc[i], __ldg(cm + jv * 256 + 32 * i), x);
+      }
+    } else {
+      for (int jv = 0; jv < nv; jv++) {
+        const vec_t x = xq[jv];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = acc_ip(acc[i], __ldg(cm + jv * 256 + 32 * i), x);
+      }
+    }
+    __syncwarp();  // every lane has read q_m (and all before it): row m may now overwrite staged floats
+#pragma unroll
+    for (int i = 0; i < 8; i++) T[m * 256 + lane + 32 * i] = is_ip ? __fsub_rn(bias, acc[i]) : acc[i];
+  }
+  __syncwarp();
+}
+
+// =====================================================================================================
+template <int M, int EPL>
+__global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const GraphDev g, const SearchParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  // warp index through a warp reduction: the compiler then knows it is warp-uniform, keeps the table base in
+  // a uniform register and folds it into the LDS address ([R + UR + imm]) -- one IADD less per lookup
+  const int warp = (int)__reduce_min_sync(FULL_MASK, threadIdx.x >> 5);
+  const int nwarps = blockDim.x >> 5;
+  constexpr int TS = M * 256;
+  constexpr int CAP = 32 * EPL;
+  float *T = reinterpret_cast<float *>(smem_raw) + (size_t)warp * TS;
+  uint64_t *tbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * TS * 4) + warp;
+  const bool fused = p.queries != nullptr;
+  uint32_t tphase = 0;
+  if (!fused) {
+    if (lane == 0) mbar_init(tbar, 1);
+    __syncwarp();
+  }
+  const int ef = p.ef;
+  const int k = p.k;
+  const bool lane0 = lane == 0;
+  const bool stats = p.out_stats != nullptr;
+  // list positions ef-1 (lowerBound once full) and ef (the slot an insertion into a full list spills to)
+  const int wl = (ef - 1) / EPL, ws = (ef - 1) % EPL;
+  // per-lane record addressing
+  const bool has_slot0 = lane < g.maxM0;
+  const uint8_t *link_base0 = g.rec0 + 4 * lane;
+  {  // keep the per-lane base as ONE 64-bit register pair (no re-derivation from the constant bank per load)
+    uint64_t t = reinterpret_cast<uint64_t>(link_base0);
+    asm volatile("" : "+l"(t));
+    link_base0 = reinterpret_cast<const uint8_t *>(t);
+  }
+  const unsigned code_delta0 = (unsigned)(g.code_off0 + lane * (M - 4));  // from a lane's link to the same lane's code row
+  const uint32_t rec0_bytes = (uint32_t)g.rec0_bytes;
+  const bool has_slotu = lane < g.maxM;
+
+  for (;;) {
+    unsigned qi = 0;
+    if (lane0) qi = atomicAdd(p.work_counter, 1u);
+    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    if (q >= p.B) break;
+    __syncwarp();  // every lane is done with the previous query's table
+    if (fused) {
+      const float *qg = p.queries + q * (int64_t)(M * p.ds);
+      if (p.cb_vec == 4) build_table<M, 4>(T, qg, p.cbt, p.ds, p.is_ip, p.bias, lane);
+      else build_table<M, 2>(T, qg, p.cbt, p.ds, p.is_ip, p.bias, lane);
+    } else {
+      if (lane0) {
+        mbar_expect_tx(tbar, (uint32_t)TS * 4u);
+        bulk_g2s(T, p.tables + q * TS, (uint32_t)TS * 4u, tbar);
+      }
+      mbar_wait(tbar, tphase);
+      tphase ^= 1u;
+    }
+    if (p.dump_tables) {  // debug export of the in-shared-memory table (parity test of the fused build)
+      float *o = p.dump_tables + q * TS;
+      for (int i = lane; i < TS; i += 32) o[i] = T[i];
+    }
+
+    // ---- greedy descent maxlevel..1 (hnswalg.h:1245-1274): after scanning one node's list the reference
+    // holds the FIRST minimum among the neighbours that beat curdist (strict <, sequential) ----
+    int hops = 0, nbrs = 0, evals = 1;
+    uint32_t cur_uk;
+    {
+      float r = 0.f;
+#pragma unroll
+      for (int m = 0; m < M; m++) r = __fadd_rn(r, T[m * 256 + g.ep_code[m]]);  // dist to the entry point (:1246)
+      cur_uk = f2u(r);
+    }
+    uint32_t rec = g.ep_rec;
+    for (int level = g.maxlevel; level > 0; level--) {
+      const uint8_t *base = g.up + g.up_off[level];
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        const uint8_t *r = base + (size_t)rec * g.recu_bytes;
+        hops++;
+        uint32_t link = EMPTY_LINK;
+        uint32_t cw[M / 4];
+#pragma unroll
+        for (int i = 0; i < M / 4; i++) cw[i] = 0u;
+        if (has_slotu) {
+          link = __ldg(reinterpret_cast<const uint32_t *>(r) + lane);
+          load_codes<M>(cw, r + g.code_offu + (size_t)lane * M);
+        }
+        const bool valid = link != EMPTY_LINK;
+        const uint32_t uk = valid ? f2u(pq_score<M>(T, cw)) : KEY_MAX;
+        const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+        nbrs += nv;
+        evals += nv;
+        const uint32_t mn = __reduce_min_sync(FULL_MASK, uk);
+        if (mn < cur_uk) {
+          const int src = __ffs(__ballot_sync(FULL_MASK, uk == mn)) - 1;  // first index wins ties
+          rec = __shfl_sync(FULL_MASK, link, src);
+          cur_uk = mn;
+          changed = true;
+        }
+      }
+      // step down: record index on the level below (node id when level == 1)
+      rec = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)rec * g.recu_bytes + g.tail_offu) + 1);
+    }
+    evals += 1;  // searchBaseLayerST re-scores the entry (:255)
+
+    // ---- level 0: searchBaseLayerST as a single sorted list in registers ----
+    uint32_t K[EPL], V[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      K[e] = KEY_MAX;
+      V[e] = 0xffffffffu;
+    }
+    if (lane0) {
+      K[0] = cur_uk;
+      V[0] = rec | EXP_BIT;  // the entry node is hop 0
+    }
+    int size = 1;
+    uint32_t worst = (ef == 1) ? cur_uk : KEY_MAX;  // lowerBound (:306); "infinite" while the list is not full
+
+    Rec<M> cur, nxt;
+    auto load_rec = [&](Rec<M> &r, uint32_t node) {
+      const uint8_t *lp = link_base0 + (size_t)node * rec0_bytes;
+      r.link = EMPTY_LINK;
+#pragma unroll
+      for (int i = 0; i < M / 4; i++) r.cw[i] = 0u;
+      if (has_slot0) {
+        r.link = __ldg(reinterpret_cast<const uint32_t *>(lp));
+        load_codes<M>(r.cw, lp + code_delta0);
+      }
+    };
+    load_rec(cur, rec);
+
+    for (;;) {
+      hops++;
+      // ---- score the neighbour list: one lane = one neighbour, m sequential ----
+      const bool valid = cur.link != EMPTY_LINK;
+      const uint32_t uk = f2u(pq_score<M>(T, cur.cw));
+      uint32_t mykey = (valid && uk < worst) ? uk : KEY_MAX;  // admission (:306) against the hop-start lowerBound
+      if (stats) {
+        const int nv = __popc(__ballot_sync(FULL_MASK, valid));
+        nbrs += nv;
+        evals += nv;
+      }
+      // ---- key of the nearest not-yet-expanded list entry == candidate_set.top() (:268) ----
+      uint32_t lm = KEY_MAX;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) lm = min(lm, K[e] | (uint32_t)((int32_t)V[e] >> 31));
+      const uint32_t e2key = __reduce_min_sync(FULL_MASK, lm);
+
+      // expand the nearest unexpanded list entry: flag it, return its node id
+      auto take_e2 = [&]() -> uint32_t {
+        const int src = __ffs(__ballot_sync(FULL_MASK, lm == e2key)) - 1;
+        uint32_t myid = 0;
+        bool done = false;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const uint32_t kk = K[e] | (uint32_t)((int32_t)V[e] >> 31);
+          if (!done && kk == e2key) {
+            myid = V[e] & IDM;
+            if (lane == src) V[e] |= EXP_BIT;
+            done = true;
+          }
+        }
+        return __shfl_sync(FULL_MASK, myid, src);
+      };
+
+      // re-encounter of a listed node?  (an id can only be listed under this very key)
+      auto listed = [&](uint32_t id) -> bool {
+        bool dup = false;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) dup |= (V[e] & IDM) == id;
+        return __any_sync(FULL_MASK, dup);
+      };
+
+      // ---- phase A: the smallest NEW candidate (if any) against the nearest unexpanded entry.  The next
+      // node is known at this point -- exactly, before anything is merged -- so its record is requested now
+      // and the DRAM round trip overlaps the insertions ----
+      bool have_new = false;
+      uint32_t mn, id = 0;
+      for (;;) {
+        mn = __reduce_min_sync(FULL_MASK, mykey);
+        if (mn == KEY_MAX) break;  // none (left) that beats lowerBound
+        const int src = __ffs(__ballot_sync(FULL_MASK, mykey == mn)) - 1;  // lower lane first among equals
+        id = __shfl_sync(FULL_MASK, cur.link, src);
+        if (lane == src) mykey = KEY_MAX;
+        if (!listed(id)) {
+          have_new = true;
+          break;
+        }
+      }
+      if (have_new && mn < e2key) {
+        load_rec(nxt, id);
+        list_insert<EPL>(K, V, mn, id | EXP_BIT, lane0);
+        size++;
+      } else {
+        if (e2key == KEY_MAX) break;  // nothing unexpanded and nothing new: candidate_set exhausted (:266)
+        load_rec(nxt, take_e2());
+        if (have_new) {
+          list_insert<EPL>(K, V, mn, id, lane0);
+          size++;
+        }
+      }
+      // ---- phase B: the other admitted candidates in lane order (equal keys keep arrival order).  lowerBound
+      // is NOT refreshed per insertion: a candidate that the falling bound would have rejected lands at a
+      // position >= ef and drops out below, exactly like the hop-start admission rule of the single-list walk ----
+      if (have_new) {
+        unsigned live = __ballot_sync(FULL_MASK, mykey != KEY_MAX);
+        while (live) {
+          const int src = __ffs(live) - 1;
+          live &= live - 1;
+          const uint32_t ck = __shfl_sync(FULL_MASK, mykey, src);
+          const uint32_t cid = __shfl_sync(FULL_MASK, cur.link, src);
+          if (listed(cid)) continue;
+          list_insert<EPL>(K, V, ck, cid, lane0);
+          size++;
+        }
+        if (size >= ef) {
+          size = ef;
+          worst = list_key_at<EPL>(K, wl, ws);  // lowerBound = top_candidates.top() (:320-321)
+          if (ef < CAP) {                        // what spilled past position ef-1 is gone
+#pragma unroll
+            for (int e = 0; e < EPL; e++)
+              if (lane * EPL + e >= ef) {
+                K[e] = KEY_MAX;
+                V[e] = 0xffffffffu;
+              }
+          }
+        }
+      }
+      cur = nxt;
+    }
+
+    // ---- results: the first k list entries, ascending (dist, label) (hnsw_bindings.cpp:346-351) ----
+    const int found = min(size, k);
+    bool tie = false;
+    const uint32_t k_next_lane = __shfl_down_sync(FULL_MASK, K[0], 1);
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int pos = lane * EPL + e;
+      if (pos < k) {
+        const bool have = pos < size;
+        p.out_dists[q * k + pos] = have ? u2f(K[e]) : CUDART_INF_F;
+        p.out_labels[q * k + pos] = have ? __ldg(g.labels + (V[e] & IDM)) : (uint64_t)UINT64_MAX;
+      }
+      const uint32_t nk = (e + 1 < EPL) ? K[e + 1 < EPL ? e + 1 : e] : k_next_lane;
+      tie |= (pos + 1 < found) && (nk == K[e]) && (e + 1 < EPL || lane < 31);
+    }
+    if (__any_sync(FULL_MASK, tie)) {
+      // rows must be ascending by (dist, label); equal distances are rare, fix them up serially
+      __syncwarp();
+      if (lane0) {
+        for (int i = 1; i < found; i++) {
+          const float d = p.out_dists[q * k + i];
+          const uint64_t l = p.out_labels[q * k + i];
+          int j = i - 1;
+          while (j >= 0 && p.out_dists[q * k + j] == d && p.out_labels[q * k + j] > l) {
+            p.out_dists[q * k + j + 1] = p.out_dists[q * k + j];
+            p.out_labels[q * k + j + 1] = p.out_labels[q * k + j];
+            j--;
+          }
+          p.out_dists[q * k + j + 1] = d;
+          p.out_labels[q * k + j + 1] = l;
+        }
+      }
+    }
+    if (lane0) {
+      p.out_found[q] = found;
+      if (stats) {
+        p.out_stats[q * 3 + 0] = hops;
+        p.out_stats[q * 3 + 1] = nbrs;
+        p.out_stats[q * 3 + 2] = evals;
+      }
+    }
+  }
+}
+
+template <int M, int EPL>
+int launch_walk4_t(annb_index *h, const SearchParams &p_in) {
+  SearchParams p = p_in;
+  constexpr int WMAX = w4_max_warps(M, EPL);
+  auto kern = hnsw_walk4<M, EPL>;
+  int warps = WMAX;
+  if (h->opt_warps_per_cta > 0) warps = (int)std::min<int64_t>(h->opt_warps_per_cta, WMAX);
+  // small batches: spread the queries over all SMs instead of filling a few of them
+  const int64_t per_sm = (p.B + h->sm_count - 1) / h->sm_count;
+  if (per_sm < warps) warps = (int)std::max<int64_t>(1, per_sm);
+  const int smem = warps * (M * 1024 + 8);
+  ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WMAX * (M * 1024 + 8)));
+  unsigned int *counter = p.work_counter;
+  if (!counter) {
+    int rc = annb_scratch(h, 4, 256, (void **)&counter);
+    if (rc) return rc;
+  }
+  ANNB_CUDA(cudaMemsetAsync(counter, 0, 8, h->stream));
+  p.work_counter = counter;
+  p.overflow_flag = reinterpret_cast<int32_t *>(counter + 1);
+  const int blocks = (int)std::min<int64_t>(h->sm_count, (p.B + warps - 1) / warps);
+  kern<<<blocks, warps * 32, smem, h->stream>>>(h->gd, p);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
+template <int M>
+int launch_walk4_m(annb_index *h, const SearchParams &p) {
+  const int epl = (p.ef + 31) / 32;
+  if (epl <= 2) return launch_walk4_t<M, 2>(h, p);
+  if (epl <= 4) return launch_walk4_t<M, 4>(h, p);
+  if (epl <= 8) return launch_walk4_t<M, 8>(h, p);
+  return launch_walk4_t<M, 16>(h, p);
+}
+
+}  // namespace
+
+// Can the plain (no filter, no deletions) search of this index run on hnsw_walk4 at all?
+bool walk4_applicable(const annb_index *h) {
+  if (h->opt_walk_kernel == 1) return false;  // A/B switch: force the round-1 kernels
+  const GraphDev &d = h->gd;
+  return h->Ks == 256 && h->code_bytes == 1 && (h->M == 8 || h->M == 16 || h->M == 32) && d.maxM0 <= 32 && d.maxM <= 32 &&
+         d.n < 0x7fffffffll;
+}
+
+// ... and may it build the tables itself from the queries (fused K1)?  Needs a vectorisable subvector
+// length and a staging layout that is consumed before it is overwritten (see build_table).
+bool walk4_can_fuse(const annb_index *h) {
+  if (h->opt_walk_kernel == 2) return false;  // A/B switch: hnsw_walk4 on materialised tables
+  if (!walk4_applicable(h) || !h->d_codebook_t || h->cb_vec == 0) return false;
+  const int M = h->M, ds = h->ds, D = M * ds;
+  const int R = (D + 255) / 256;
+  if (R > M) return false;
+  for (int t = 0; t + 1 < R; t++)
+    if ((t + 1) * 256 > (M - R + t + 1) * ds) return false;
+  return true;
+}
+
+int launch_walk4(annb_index *h, const SearchParams &p) {
+  if (p.B == 0) return ANNB_OK;
+  if (!p.queries && (reinterpret_cast<uintptr_t>(p.tables) & 15)) return 1;  // TMA needs 16-byte alignment
+  if (p.ef > ANNB_MAX_EF) ANNB_FAIL(ANNB_ELIMIT, "ef=%d exceeds ANNB_MAX_EF=%d", p.ef, ANNB_MAX_EF);
+  switch (h->M) {
+    case 8: return launch_walk4_m<8>(h, p);
+    case 16: return launch_walk4_m<16>(h, p);
+    case 32: return launch_walk4_m<32>(h, p);
+  }
+  return 1;
+}
