@@ -59,6 +59,8 @@ PROTOTYPES = {
     'annb_search_submit': (_int, [_vp, _vp, _int, _i64, _int, _int, _int, _vp, _vp, _int, C.POINTER(_int)]),
     'annb_search_wait': (_int, [_vp, _int]),
     'annb_merge_topk': (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
+    'annb_merge_topk_packed': (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _vp, _vp, _int]),
+    'annb_lane_stream': (_int, [_vp, _int, C.POINTER(_u64)]),
     'annb_last_kernel_ms': (_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'annb_launch_count': (_int, [_vp, C.POINTER(_i64)]),
     'annb_fallback_count': (_int, [_vp, C.POINTER(_i64)]),

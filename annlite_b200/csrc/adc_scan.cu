@@ -274,13 +274,72 @@ int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int
   return ANNB_OK;
 }
 
-int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k,
-                      uint64_t *labels_out, float *dists_out) {
+// Shard merge (container.py:130-138 with the (dist, label) order): G ascending lists of k per query, given as two
+// strided arrays so that the all-gathered PACKED per-rank buffers ([B*k dists][B*k labels] per rank, one NCCL
+// all-gather) are merged in place.  One warp per query: the G*k pairs are staged in shared memory, then every
+// pair finds its global rank = its own position + sum over the other lists of a binary search (lists are sorted),
+// O(G*k*G*log k / 32) per query instead of the all-pairs count.
+__global__ void merge_sorted_kernel(const float *__restrict__ d_in, const uint64_t *__restrict__ l_in, int G, int64_t B, int k,
+                                    int64_t d_gstride, int64_t l_gstride, float *__restrict__ d_out,
+                                    uint64_t *__restrict__ l_out) {
+  extern __shared__ __align__(16) unsigned char msm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * nwarps + warp;
+  if (b >= B) return;
+  const int total = G * k;
+  uint64_t *sl = reinterpret_cast<uint64_t *>(msm) + (size_t)warp * total;
+  float *sd = reinterpret_cast<float *>(msm + (size_t)nwarps * total * 8) + (size_t)warp * total;
+  for (int x = lane; x < total; x += 32) {
+    const int g = x / k, p = x - g * k;
+    sd[x] = d_in[g * d_gstride + b * k + p];
+    sl[x] = l_in[g * l_gstride + b * k + p];
+  }
+  __syncwarp();
+  int valid = 0;
+  for (int x = lane; x < total; x += 32) {
+    const uint64_t lx = sl[x];
+    if (lx == UINT64_MAX) continue;  // a shard that found fewer than k
+    valid++;
+    const int gx = x / k;
+    const float dx = sd[x];
+    int rank = x - gx * k;  // pairs before it in its own (sorted) list
+    for (int g = 0; g < G; g++) {
+      if (g == gx) continue;
+      // number of pairs of list g that precede (dx, lx): order (dist, label), equal pairs by list index
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float dm = sd[g * k + mid];
+        const uint64_t lm = sl[g * k + mid];
+        const bool before = lm != UINT64_MAX && (dm < dx || (dm == dx && (lm < lx || (lm == lx && g < gx))));
+        if (before) lo = mid + 1;
+        else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      d_out[b * k + rank] = dx;
+      l_out[b * k + rank] = lx;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(FULL_MASK, valid, o);
+  for (int p = valid + lane; p < k; p += 32) {
+    d_out[b * k + p] = CUDART_INF_F;
+    l_out[b * k + p] = UINT64_MAX;
+  }
+}
+
+int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k, int64_t l_gstride,
+                      int64_t d_gstride, uint64_t *labels_out, float *dists_out, cudaStream_t stream) {
   if (B == 0) return ANNB_OK;
-  const int warps = 4;
-  // shard results laid out [g][b][k] => g_stride = B*k, b_stride = k
-  merge_topk_kernel<uint64_t, uint64_t, 1><<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, h->stream>>>(
-      dists, labels, G, B, k, B * (int64_t)k, (int64_t)k, dists_out, labels_out, (uint64_t)UINT64_MAX, (uint64_t)UINT64_MAX);
+  const size_t per_warp = (size_t)G * k * 12;
+  if (per_warp > 200 * 1024) ANNB_FAIL(ANNB_ELIMIT, "G*k=%d is too large for the shard merge", G * k);
+  int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (96 * 1024) / per_warp));
+  const size_t smem = warps * per_warp;
+  if (smem > 48 * 1024) ANNB_CUDA(cudaFuncSetAttribute(merge_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_sorted_kernel<<<(unsigned)((B + warps - 1) / warps), warps * 32, smem, stream>>>(dists, labels, G, B, k, d_gstride, l_gstride,
+                                                                                       dists_out, labels_out);
   h->launches++;
   ANNB_CUDA(cudaGetLastError());
   return ANNB_OK;

@@ -118,6 +118,7 @@ struct SearchParams {
   int ds;               // subvector length
   int is_ip;            // IP / COSINE table form: bias - <cb, q>
   float bias;           // fp32(1/Ks), or 0 for the raw pq_bind form
+  int prefetch;         // hnsw_walk4 L2 prefetch: bit 0 = the nearest unexpanded entry at hop start, bit 1 = candidates closer than it
   float *dump_tables;   // debug: (B, M, Ks) device buffer that receives the tables the walk used, or nullptr
   int64_t B;
   int k, ef;
@@ -199,6 +200,7 @@ struct annb_index {
   int64_t opt_ip_raw = 0;          // K1 IP form without the 1/Ks bias: T = 0 - ip (pq_bind compatibility)
   int64_t opt_walk_kernel = 0;     // plain search: 0 = hnsw_walk4 with fused K1 (default), 1 = round-1 kernels (K1 +
                                    // hnsw_walk_fast), 2 = hnsw_walk4 over materialised tables (K1 + TMA staging)
+  int64_t opt_prefetch = 1;        // hnsw_walk4 record L2 prefetch (bit mask, see SearchParams::prefetch)
   int64_t opt_dump_tables = 0;     // device pointer: searches copy the tables they used there (debug / parity tests)
 };
 
@@ -219,8 +221,9 @@ int launch_search(annb_index *h, const SearchParams &p, int mode);
 bool walk4_applicable(const annb_index *h);
 bool walk4_can_fuse(const annb_index *h);
 int launch_walk4(annb_index *h, const SearchParams &p);
-int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k,
-                      uint64_t *labels_out, float *dists_out);
+// G ascending (dist, label) lists of k per query -> global k best; *_gstride = distance between two shards' arrays in elements
+int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k, int64_t l_gstride,
+                      int64_t d_gstride, uint64_t *labels_out, float *dists_out, cudaStream_t stream);
 int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t n_filter, uint32_t *d_by_label,
                          uint32_t *d_by_id);
 

@@ -1221,7 +1221,28 @@ int annb_merge_topk(annb_index_t *h, const uint64_t *labels_gbk, const float *di
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
   if (!labels_gbk || !dists_gbk || !labels_out || !dists_out || G <= 0 || k <= 0 || B < 0) ANNB_FAIL(ANNB_EINVAL, "bad arguments");
-  return launch_merge_topk(h, labels_gbk, dists_gbk, G, B, k, labels_out, dists_out);
+  return launch_merge_topk(h, labels_gbk, dists_gbk, G, B, k, B * (int64_t)k, B * (int64_t)k, labels_out, dists_out, h->stream);
+}
+
+int annb_merge_topk_packed(annb_index_t *h, const void *packed, int G, int64_t B, int k, int64_t rank_stride_bytes,
+                           int64_t labels_offset_bytes, uint64_t *labels_out, float *dists_out, int lane) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (!packed || !labels_out || !dists_out || G <= 0 || k <= 0 || B < 0 || lane < 0 || lane > 1)
+    ANNB_FAIL(ANNB_EINVAL, "bad arguments");
+  if ((rank_stride_bytes & 7) || (labels_offset_bytes & 7) || labels_offset_bytes < B * (int64_t)k * 4 ||
+      rank_stride_bytes < labels_offset_bytes + B * (int64_t)k * 8 || (reinterpret_cast<uintptr_t>(packed) & 7))
+    ANNB_FAIL(ANNB_EINVAL, "packed shard results: offsets must be 8-byte aligned and hold (B,k) fp32 + (B,k) u64");
+  const float *d = reinterpret_cast<const float *>(packed);
+  const uint64_t *l = reinterpret_cast<const uint64_t *>(reinterpret_cast<const uint8_t *>(packed) + labels_offset_bytes);
+  return launch_merge_topk(h, l, d, G, B, k, rank_stride_bytes / 8, rank_stride_bytes / 4, labels_out, dists_out,
+                           lane ? h->stream2 : h->stream);
+}
+
+int annb_lane_stream(annb_index_t *h, int lane, uint64_t *stream_out) {
+  if (!h || !stream_out || lane < 0 || lane > 1) ANNB_FAIL(ANNB_EINVAL, "bad arguments");
+  *stream_out = (uint64_t)(uintptr_t)(lane ? h->stream2 : h->stream);
+  return ANNB_OK;
 }
 
 int annb_last_kernel_ms(annb_index_t *h, float *table_ms, float *search_ms, float *scan_ms) {
@@ -1260,6 +1281,7 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "flagged_epl")) h->opt_flagged_epl = value;
   else if (!strcmp(name, "walk_kernel")) h->opt_walk_kernel = value;
   else if (!strcmp(name, "dump_tables")) h->opt_dump_tables = value;
+  else if (!strcmp(name, "prefetch")) h->opt_prefetch = value;
   else if (!strcmp(name, "reset_counters")) h->flagged_fallbacks = 0;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;

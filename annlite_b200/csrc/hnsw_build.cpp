@@ -4,7 +4,7 @@
 // Construction is the SURVEY.md section 8f "next" row 2: a host C++ implementation that follows
 // the reference's insertion algorithm (include/hnswlib/hnswalg.h:1108-1235 addPoint, :158-238
 // searchBaseLayer, :443-483 getNeighborsByHeuristic2, :502-619 mutuallyConnectNewElement) closely
-// enough that a single-threaded build produces a byte-identical graph (tests/test_build_parity.py
+// enough that a single-threaded build produces a byte-identical graph (tests/test_host_graph.py, tests/test_update_parity.py
 // compares against a graph the compiled reference built from the same inputs).  That includes
 // the reference's PQ-mode quirk: PQLookup ignores its first argument, so
 // every "distance between two stored nodes" is really the distance from the point being inserted

@@ -114,6 +114,24 @@ __device__ __forceinline__ void load_table(float *dst, const float *__restrict__
   }
 }
 
+// Next query of the persistent loop: ONE lane bumps the work counter (a predicated instruction, not a branch) and
+// the value is spread with a warp REDUCTION: REDUX delivers it in a uniform register, so ptxas can prove that the
+// loop exit is warp-uniform.  With `__shfl_sync(qi, 0)` it cannot, and then guards every warp-level operation of the
+// loop body with a BRA.DIV convergence check.
+__device__ __forceinline__ int64_t next_query(unsigned int *counter, int lane) {
+  unsigned qi = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.eq.u32 p, %2, 0;\n"
+      "@p atom.global.add.u32 %0, [%1], 1;\n"
+      "}\n"
+      : "+r"(qi)
+      : "l"(counter), "r"(lane)
+      : "memory");
+  return (int64_t)__reduce_max_sync(FULL_MASK, qi);
+}
+
 struct Walk {
   uint32_t node;   // node reached on level 0
   float dist;      // its distance
@@ -246,9 +264,7 @@ __global__ void hnsw_walk_chunked(const GraphDev g, const SearchParams p, const 
   const int ef = p.ef;
 
   for (;;) {
-    unsigned qi = 0;
-    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
-    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    const int64_t q = next_query(p.work_counter, lane);
     if (q >= p.B) break;
     const float *T;
     if (SMEM_TABLE) {
@@ -334,9 +350,7 @@ __global__ void hnsw_walk_fast(const GraphDev g, const SearchParams p, const int
   constexpr int CW = CR > 0 ? CR / 4 : 1;
 
   for (;;) {
-    unsigned qi = 0;
-    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
-    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    const int64_t q = next_query(p.work_counter, lane);
     if (q >= p.B) break;
     const float *T;
     if (SMEM_TABLE) {
@@ -594,9 +608,7 @@ __global__ void hnsw_walk_flagged(const GraphDev g, const SearchParams p, const 
   const float FLT_MAX_ = 3.402823466e+38f;
 
   for (;;) {
-    unsigned qi = 0;
-    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
-    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    const int64_t q = next_query(p.work_counter, lane);
     if (q >= p.B) break;
     __syncwarp();
     if (tma_table) {
@@ -915,9 +927,7 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
   const bool use_filter = filter != nullptr;
 
   for (;;) {
-    unsigned qi = 0;
-    if (lane == 0) qi = atomicAdd(p.work_counter, 1u);
-    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    const int64_t q = next_query(p.work_counter, lane);
     if (q >= p.B) break;
     const float *T;
     if (SMEM_TABLE) {

@@ -47,7 +47,6 @@ constexpr uint32_t EMPTY_LINK = 0xffffffffu;
 constexpr uint32_t EXP_BIT = 0x80000000u;   // list value: node already expanded (empty slots carry it too)
 constexpr uint32_t IDM = 0x7fffffffu;
 constexpr uint32_t KEY_MAX = 0xffffffffu;   // above the image of every finite distance and of +inf
-constexpr int W4_SMEM_OPTIN = 232448;       // 227 KB: the largest dynamic shared-memory size of one CTA
 
 // order-preserving map fp32 -> u32 (a < b  <=>  f2u(a) < f2u(b) for non-NaN, no -0.0: the ADC sum starts
 // at +0.f and x + (-0) never yields -0)
@@ -59,10 +58,28 @@ __device__ __forceinline__ float u2f(uint32_t u) {
   return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u));
 }
 
-constexpr int w4_max_warps(int M, int EPL) {
-  const int by_smem = W4_SMEM_OPTIN / (M * 1024 + 8);
-  const int by_regs = EPL <= 4 ? 28 : (EPL == 8 ? 20 : 14);
-  return by_smem < by_regs ? by_smem : by_regs;
+// Launch geometry.  Shared memory per query = its table (M KB); the TMA form adds one 8-byte mbarrier per warp.
+// An SM has 228 KB of shared memory and every resident CTA costs 1 KB on top of what it asks for, so at M=8
+// 4 CTAs x 7 warps x 8 KB + 4 KB fills it to the byte: 28 queries per SM in CTAs small enough that the tail of one
+// launch frees SMs piecewise for the next (the two lanes of annb_search_submit overlap that way).  The TMA form
+// (8 bytes more per warp) runs 3 CTAs x 9 warps = 27.  Wider lists need more registers: fewer warps.
+constexpr int W4_SMEM_SM = 233472;  // 228 KB per SM
+constexpr int w4_cta_warps(int M, int EPL, bool fused) {
+  return M == 8 ? (EPL <= 4 ? (fused ? 7 : 9) : (EPL == 8 ? 5 : 7)) : 7;
+}
+constexpr int w4_ctas(int M, int EPL, bool fused) {
+  return M == 8 ? (EPL <= 4 ? (fused ? 4 : 3) : (EPL == 8 ? 4 : 2)) : (M == 16 ? 2 : 1);
+}
+constexpr int w4_smem(int M, int EPL, bool fused) { return w4_cta_warps(M, EPL, fused) * (M * 1024 + (fused ? 0 : 8)); }
+constexpr bool w4_fits(int M, int EPL, bool fused) {
+  return w4_ctas(M, EPL, fused) * (w4_smem(M, EPL, fused) + 1024) <= W4_SMEM_SM;
+}
+constexpr int w4_max_threads(int M, int EPL) {
+  return 32 * (w4_cta_warps(M, EPL, true) > w4_cta_warps(M, EPL, false) ? w4_cta_warps(M, EPL, true) : w4_cta_warps(M, EPL, false));
+}
+constexpr int w4_min_ctas(int M, int EPL) {  // register cap = 64K / (max threads x this): must allow either residency
+  const int tf = w4_ctas(M, EPL, true) * w4_cta_warps(M, EPL, true) * 32, tt = w4_ctas(M, EPL, false) * w4_cta_warps(M, EPL, false) * 32;
+  return (tf > tt ? tf : tt) / w4_max_threads(M, EPL);
 }
 
 // ---- one level-0 record in registers: lane j holds link j and the M code bytes of neighbour j ----
@@ -200,7 +217,7 @@ __device__ __forceinline__ void build_table(float *T, const float *__restrict__ 
 
 // =====================================================================================================
 template <int M, int EPL>
-__global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const GraphDev g, const SearchParams p) {
+__global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) hnsw_walk4(const GraphDev g, const SearchParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   // warp index through a warp reduction: the compiler then knows it is warp-uniform, keeps the table base in
@@ -236,9 +253,21 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
   const bool has_slotu = lane < g.maxM;
 
   for (;;) {
+    // next query: ONE lane bumps the work counter and the value is spread with a warp REDUCTION, not a shuffle:
+    // REDUX delivers it in a uniform register, so ptxas can prove that the loop exit below is warp-uniform.
+    // With `__shfl_sync(qi, 0)` it cannot, and then guards every warp-level operation of the whole loop body with
+    // a BRA.DIV convergence check (31 sites, ~25 extra warp instructions per hop).
     unsigned qi = 0;
-    if (lane0) qi = atomicAdd(p.work_counter, 1u);
-    const int64_t q = __shfl_sync(FULL_MASK, qi, 0);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.u32 p, %2, 0;\n"
+        "@p atom.global.add.u32 %0, [%1], 1;\n"
+        "}\n"
+        : "+r"(qi)
+        : "l"(p.work_counter), "r"(lane)
+        : "memory");
+    const int64_t q = __reduce_max_sync(FULL_MASK, qi);
     if (q >= p.B) break;
     __syncwarp();  // every lane is done with the previous query's table
     if (fused) {
@@ -316,7 +345,7 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
     int size = 1;
     uint32_t worst = (ef == 1) ? cur_uk : KEY_MAX;  // lowerBound (:306); "infinite" while the list is not full
 
-    Rec<M> cur, nxt;
+    Rec<M> recA, recB;
     auto load_rec = [&](Rec<M> &r, uint32_t node) {
       const uint8_t *lp = link_base0 + (size_t)node * rec0_bytes;
       r.link = EMPTY_LINK;
@@ -327,10 +356,45 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
         load_codes<M>(r.cw, lp + code_delta0);
       }
     };
-    load_rec(cur, rec);
+    load_rec(recA, rec);
 
-    for (;;) {
+    // One hop: `cur` holds the record of the node being expanded, `nxt` receives the record of the next one.
+    // The two record register sets alternate roles (no copy, so nothing waits on a load before it is needed).
+    auto hop = [&](Rec<M> &cur, Rec<M> &nxt) -> bool {
       hops++;
+      // ---- nearest not-yet-expanded list entry == candidate_set.top() (:268).  It is the next node unless this
+      // hop finds something closer, so its record is pulled into L2 FIRST: the DRAM round trip then overlaps the
+      // whole hop, and a wrong guess still leaves the record in L2 for the hop that does expand it ----
+      uint32_t lm = KEY_MAX;
+#pragma unroll
+      for (int e = 0; e < EPL; e++) lm = min(lm, K[e] | (uint32_t)((int32_t)V[e] >> 31));
+      const uint32_t e2key = __reduce_min_sync(FULL_MASK, lm);
+      int e2src = 0;
+      uint32_t e2id = 0;
+      if (e2key != KEY_MAX) {
+        e2src = __ffs(__ballot_sync(FULL_MASK, lm == e2key)) - 1;
+        uint32_t myid = 0;
+#pragma unroll
+        for (int e = EPL - 1; e >= 0; e--)
+          if ((K[e] | (uint32_t)((int32_t)V[e] >> 31)) == e2key) myid = V[e] & IDM;  // lowest matching slot wins
+        e2id = __shfl_sync(FULL_MASK, myid, e2src);
+        // (an L2 prefetch, not a register load: a second load into the same registers would have to wait for
+        // this one to land whenever a new candidate wins)
+        if ((p.prefetch & 1) && lane * 128u < rec0_bytes) prefetch_l2(g.rec0 + (size_t)e2id * rec0_bytes + lane * 128u);
+      }
+      // expand that entry: flag it (the lowest matching slot of lane e2src)
+      auto take_e2 = [&]() {
+        if (lane == e2src) {
+          bool done = false;
+#pragma unroll
+          for (int e = 0; e < EPL; e++) {
+            const bool hit = !done && (K[e] | (uint32_t)((int32_t)V[e] >> 31)) == e2key;
+            if (hit) V[e] |= EXP_BIT;
+            done |= hit;
+          }
+        }
+      };
+
       // ---- score the neighbour list: one lane = one neighbour, m sequential ----
       const bool valid = cur.link != EMPTY_LINK;
       const uint32_t uk = f2u(pq_score<M>(T, cur.cw));
@@ -340,28 +404,11 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
         nbrs += nv;
         evals += nv;
       }
-      // ---- key of the nearest not-yet-expanded list entry == candidate_set.top() (:268) ----
-      uint32_t lm = KEY_MAX;
-#pragma unroll
-      for (int e = 0; e < EPL; e++) lm = min(lm, K[e] | (uint32_t)((int32_t)V[e] >> 31));
-      const uint32_t e2key = __reduce_min_sync(FULL_MASK, lm);
-
-      // expand the nearest unexpanded list entry: flag it, return its node id
-      auto take_e2 = [&]() -> uint32_t {
-        const int src = __ffs(__ballot_sync(FULL_MASK, lm == e2key)) - 1;
-        uint32_t myid = 0;
-        bool done = false;
-#pragma unroll
-        for (int e = 0; e < EPL; e++) {
-          const uint32_t kk = K[e] | (uint32_t)((int32_t)V[e] >> 31);
-          if (!done && kk == e2key) {
-            myid = V[e] & IDM;
-            if (lane == src) V[e] |= EXP_BIT;
-            done = true;
-          }
-        }
-        return __shfl_sync(FULL_MASK, myid, src);
-      };
+      if ((p.prefetch & 2) && mykey < e2key) {
+        // closer than everything still unexpanded: (one of) the next node(s) -- warm its record in L2 now
+        const uint8_t *rp = g.rec0 + (size_t)cur.link * rec0_bytes;
+        for (uint32_t o = 0; o < rec0_bytes; o += 128) prefetch_l2(rp + o);
+      }
 
       // re-encounter of a listed node?  (an id can only be listed under this very key)
       auto listed = [&](uint32_t id) -> bool {
@@ -371,9 +418,8 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
         return __any_sync(FULL_MASK, dup);
       };
 
-      // ---- phase A: the smallest NEW candidate (if any) against the nearest unexpanded entry.  The next
-      // node is known at this point -- exactly, before anything is merged -- so its record is requested now
-      // and the DRAM round trip overlaps the insertions ----
+      // ---- phase A: the smallest NEW candidate (if any) against the nearest unexpanded entry: the next node is
+      // known exactly, before anything is merged ----
       bool have_new = false;
       uint32_t mn, id = 0;
       for (;;) {
@@ -388,12 +434,13 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
         }
       }
       if (have_new && mn < e2key) {
-        load_rec(nxt, id);
+        load_rec(nxt, id);  // replaces the guess; its DRAM round trip overlaps the insertions below
         list_insert<EPL>(K, V, mn, id | EXP_BIT, lane0);
         size++;
       } else {
-        if (e2key == KEY_MAX) break;  // nothing unexpanded and nothing new: candidate_set exhausted (:266)
-        load_rec(nxt, take_e2());
+        if (e2key == KEY_MAX) return false;  // nothing unexpanded and nothing new: candidate_set exhausted (:266)
+        load_rec(nxt, e2id);
+        take_e2();
         if (have_new) {
           list_insert<EPL>(K, V, mn, id, lane0);
           size++;
@@ -426,7 +473,11 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
           }
         }
       }
-      cur = nxt;
+      return true;
+    };
+    for (;;) {
+      if (!hop(recA, recB)) break;
+      if (!hop(recB, recA)) break;
     }
 
     // ---- results: the first k list entries, ascending (dist, label) (hnsw_bindings.cpp:346-351) ----
@@ -476,15 +527,23 @@ __global__ void __launch_bounds__(32 * w4_max_warps(M, EPL), 1) hnsw_walk4(const
 template <int M, int EPL>
 int launch_walk4_t(annb_index *h, const SearchParams &p_in) {
   SearchParams p = p_in;
-  constexpr int WMAX = w4_max_warps(M, EPL);
+  p.prefetch = (int)h->opt_prefetch;
+  static_assert(w4_fits(M, EPL, true) && w4_fits(M, EPL, false), "walk4 geometry exceeds the SM's shared memory");
   auto kern = hnsw_walk4<M, EPL>;
-  int warps = WMAX;
-  if (h->opt_warps_per_cta > 0) warps = (int)std::min<int64_t>(h->opt_warps_per_cta, WMAX);
+  const bool fused = p.queries != nullptr;
+  int warps = fused ? w4_cta_warps(M, EPL, true) : w4_cta_warps(M, EPL, false);
+  int ctas = fused ? w4_ctas(M, EPL, true) : w4_ctas(M, EPL, false);
+  if (h->opt_warps_per_cta > 0) warps = (int)std::min<int64_t>(h->opt_warps_per_cta, warps);
+  if (h->opt_ctas_per_sm > 0) ctas = (int)std::min<int64_t>(h->opt_ctas_per_sm, ctas);
   // small batches: spread the queries over all SMs instead of filling a few of them
   const int64_t per_sm = (p.B + h->sm_count - 1) / h->sm_count;
-  if (per_sm < warps) warps = (int)std::max<int64_t>(1, per_sm);
-  const int smem = warps * (M * 1024 + 8);
-  ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WMAX * (M * 1024 + 8)));
+  if (per_sm < (int64_t)warps * ctas) {
+    ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (per_sm + warps - 1) / warps));
+    if (ctas == 1) warps = (int)std::max<int64_t>(1, std::min<int64_t>(warps, per_sm));
+  }
+  const int smem = warps * (M * 1024 + (fused ? 0 : 8));
+  ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 std::max(w4_smem(M, EPL, true), w4_smem(M, EPL, false))));
   unsigned int *counter = p.work_counter;
   if (!counter) {
     int rc = annb_scratch(h, 4, 256, (void **)&counter);
@@ -493,7 +552,7 @@ int launch_walk4_t(annb_index *h, const SearchParams &p_in) {
   ANNB_CUDA(cudaMemsetAsync(counter, 0, 8, h->stream));
   p.work_counter = counter;
   p.overflow_flag = reinterpret_cast<int32_t *>(counter + 1);
-  const int blocks = (int)std::min<int64_t>(h->sm_count, (p.B + warps - 1) / warps);
+  const int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * ctas, (p.B + warps - 1) / warps);
   kern<<<blocks, warps * 32, smem, h->stream>>>(h->gd, p);
   h->launches++;
   ANNB_CUDA(cudaGetLastError());

@@ -255,7 +255,13 @@ class Engine:
                                              C.byref(t)))
         self._inflight = getattr(self, '_inflight', {})
         self._inflight[t.value] = (k0, k1, k2)      # keep the buffers alive
+        self._next_ticket = t.value + 1
         return t.value
+
+    @property
+    def next_lane(self):
+        """Internal lane (0/1 = stream) the next search_submit will use: tickets alternate."""
+        return getattr(self, '_next_ticket', 0) & 1
 
     def search_wait(self, ticket):
         try:
@@ -267,6 +273,16 @@ class Engine:
         G, B, k = labels_gbk.shape
         L.check(self._lib.annb_merge_topk(self._h, labels_gbk.data_ptr(), dists_gbk.data_ptr(), G, B, k,
                                           out_labels.data_ptr(), out_dists.data_ptr()))
+
+    def merge_topk_packed(self, gathered, G, B, k, rank_stride_bytes, labels_offset_bytes, out_labels, out_dists, lane):
+        """Merge G all-gathered packed shard results ([dists | labels] per rank) on lane `lane`'s stream."""
+        L.check(self._lib.annb_merge_topk_packed(self._h, gathered.data_ptr(), int(G), int(B), int(k), int(rank_stride_bytes),
+                                                 int(labels_offset_bytes), out_labels.data_ptr(), out_dists.data_ptr(), int(lane)))
+
+    def lane_stream(self, lane):
+        s = C.c_uint64()
+        L.check(self._lib.annb_lane_stream(self._h, int(lane), C.byref(s)))
+        return s.value
 
     # ---- misc ---------------------------------------------------------------------------
     def sync(self):

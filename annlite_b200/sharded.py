@@ -77,3 +77,59 @@ class ShardedSearcher:
             return self.merge(gl, gd, k)
         ml, md = merge_topk_host(gl.cpu().numpy().view(np.uint64), gd.cpu().numpy(), k)
         return ml, md
+
+
+class ShardedEngine:
+    """The sharded search step on one GPU of G (one process per GPU, NCCL): walk of this rank's shard, ONE
+    all-gather of the packed (B,k) {fp32 dist, u64 label} results, merge -- all enqueued on one stream of the
+    Engine, no host synchronisation in between, two batches in flight (the walk of batch i+1 hides the gather and
+    merge of batch i).  Merge rule = annlite/container.py:130-138 with (dist, label) order.
+
+    Every rank must call submit() in the same order (the all-gathers of one process group are matched by order)."""
+
+    def __init__(self, engine, B, k, group=None):
+        import torch
+        import torch.distributed as dist
+        self.e, self.B, self.k, self.group = engine, int(B), int(k), group
+        self.world = dist.get_world_size(group)
+        self.off_l = (self.B * self.k * 4 + 7) // 8 * 8
+        self.stride = self.off_l + self.B * self.k * 8
+        dev = torch.device('cuda', engine.device)
+        self.packed = [torch.zeros(self.stride, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.gathered = [torch.zeros(self.world * self.stride, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.out_l = [torch.empty((self.B, self.k), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.out_d = [torch.empty((self.B, self.k), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.streams = [torch.cuda.ExternalStream(engine.lane_stream(i), device=dev) for i in range(2)]
+
+    def views(self, lane):
+        n = self.B * self.k
+        p = self.packed[lane]
+        import torch
+        return (p[self.off_l:self.off_l + n * 8].view(torch.int64).view(self.B, self.k),
+                p[:n * 4].view(torch.float32).view(self.B, self.k))
+
+    def submit(self, queries, ef, normalize=0, host_labels=None, host_dists=None):
+        """queries: (B, D) device tensor or pinned host array, the same on every rank.  Returns a ticket; the
+        merged result of that ticket is in .result(ticket) (device) and, if given, in the pinned host tensors."""
+        import torch
+        import torch.distributed as dist
+        lane = self.e.next_lane
+        lv, dv = self.views(lane)
+        t = self.e.search_submit(queries, lv, dv, k=self.k, ef=ef, normalize=normalize)
+        assert (t & 1) == lane
+        with torch.cuda.stream(self.streams[lane]):
+            dist.all_gather_into_tensor(self.gathered[lane], self.packed[lane], group=self.group)
+        self.e.merge_topk_packed(self.gathered[lane], self.world, self.B, self.k, self.stride, self.off_l,
+                                 self.out_l[lane], self.out_d[lane], lane)
+        if host_labels is not None:
+            with torch.cuda.stream(self.streams[lane]):
+                host_labels.copy_(self.out_l[lane], non_blocking=True)
+                host_dists.copy_(self.out_d[lane], non_blocking=True)
+        return t
+
+    def wait(self, ticket):
+        self.e.search_wait(ticket)
+
+    def result(self, ticket):
+        lane = ticket & 1
+        return self.out_l[lane], self.out_d[lane]

@@ -229,6 +229,17 @@ ANNB_API int annb_search_wait(annb_index_t *h, int ticket);
 ANNB_API int annb_merge_topk(annb_index_t *h, const uint64_t *labels_gbk, const float *dists_gbk, int G,
                     int64_t B, int k, uint64_t *labels_out, float *dists_out);
 
+/* The sharded step without a host synchronisation (annlite/container.py:88-144 spread over G GPUs): a rank's
+ * walk (annb_search_submit with DEVICE outputs) writes its (B,k) fp32 distances and (B,k) u64 labels into ONE
+ * packed buffer ([dists | pad to 8][labels], rank_stride_bytes long), ONE all-gather of that buffer over NCCL is
+ * enqueued on the same lane's stream (annb_lane_stream(ticket & 1) -> torch.cuda.ExternalStream), and
+ * annb_merge_topk_packed enqueues the merge of the G gathered buffers on that stream again.  annb_search_wait
+ * (ticket) then covers walk + gather + merge.  `lane` = ticket & 1. */
+ANNB_API int annb_merge_topk_packed(annb_index_t *h, const void *packed_gathered, int G, int64_t B, int k,
+                           int64_t rank_stride_bytes, int64_t labels_offset_bytes, uint64_t *labels_out,
+                           float *dists_out, int lane);
+ANNB_API int annb_lane_stream(annb_index_t *h, int lane, uint64_t *stream_out);
+
 /* ---- introspection for bench / roofline ------------------------------------------------------ */
 /* Device time of the last search / scan / table kernel in milliseconds (CUDA events on the
  * handle's stream) and launch counters since creation. */

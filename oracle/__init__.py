@@ -3,7 +3,7 @@
 A plain-C restatement (``oracle/pq_oracle.c`` -> ``oracle/liborc.so``) of the reference's
 algorithm, wrapped with ctypes.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import this package, and only as the checker;
-``annlite_b200`` never does (tests/test_no_oracle_in_product.py enforces it).
+``annlite_b200`` never does (tests/test_abi_and_isolation.py enforces it).
 
 Besides the restatement, ``pq_oracle.c`` carries two functions that are NOT the reference's algorithm and
 say so: ``orc_single_list_walk`` / ``orc_flagged_walk``, scalar models of the product's visited-free walks.

@@ -1,6 +1,6 @@
 """CPU, world_size 2, gloo: host logic of the sharded layout (range split, all-gather, merge rule).
 The local searcher here is the oracle over each rank's shard graph (test infrastructure); on the
-GPU the same ShardedSearcher is fed Engine.search / Engine.merge_topk (tests/test_gpu_multi.py)."""
+GPU the same split runs as ShardedEngine: walk, one NCCL all-gather, merge kernel (tests/test_gpu_multi.py, 2 ranks)."""
 import os
 import socket
 import sys
