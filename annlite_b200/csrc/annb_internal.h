@@ -118,6 +118,7 @@ struct SearchParams {
   int ds;               // subvector length
   int is_ip;            // IP / COSINE table form: bias - <cb, q>
   float bias;           // fp32(1/Ks), or 0 for the raw pq_bind form
+  int out_internal;     // hnsw_walk4: write internal node ids instead of labels into out_labels (the GPU builder)
   int prefetch;         // hnsw_walk4 L2 prefetch: bit 0 = the nearest unexpanded entry at hop start, bit 1 = candidates closer than it
   float *dump_tables;   // debug: (B, M, Ks) device buffer that receives the tables the walk used, or nullptr
   int64_t B;
@@ -201,11 +202,27 @@ struct annb_index {
   int64_t opt_walk_kernel = 0;     // plain search: 0 = hnsw_walk4 with fused K1 (default), 1 = round-1 kernels (K1 +
                                    // hnsw_walk_fast), 2 = hnsw_walk4 over materialised tables (K1 + TMA staging)
   int64_t opt_prefetch = 1;        // hnsw_walk4 record L2 prefetch (bit mask, see SearchParams::prefetch)
+  int64_t opt_gpu_build = 1;       // add_items with num_threads != 1 and >= 16384 fresh rows: level-0 insertion on the GPU
+  int64_t opt_gpu_build_frac = 16; // a GPU-built batch is at most 1/frac of the graph it is inserted into
+  int64_t reserve_nodes = 0;       // sync_device_graph sizes the device graph for this many nodes (GPU builder)
   int64_t opt_dump_tables = 0;     // device pointer: searches copy the tables they used there (debug / parity tests)
 };
 
 int annb_scratch(annb_index *h, int slot, size_t bytes, void **out);
 int annb_pinned(annb_index *h, int slot, size_t bytes, void **out);
+
+#define ANNB_TRY_RC(expr)    \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+// scratch slots (annb_scratch)
+enum {
+  S_QUERIES = 0, S_TABLES, S_OUT_D, S_OUT_L, S_COUNTER, S_VISITED, S_TOUCHED, S_CAND,
+  S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I,
+  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS
+};
 
 // kernels (launchers)
 int launch_l2_normalize(annb_index *h, float *x, int64_t B, int D);
@@ -229,5 +246,13 @@ int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t
 
 // host builder
 int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels, int64_t n, int num_threads,
-                     const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows);
+                     const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows,
+                     const int32_t *forced_levels = nullptr);
+// the next n levels the index's generator would hand out (getRandomLevel, hnswalg.h:151-155), in order
+int hnsw_draw_levels(annb_index *h, int64_t n, int32_t *out);
+// annb_add_items without the handle lock (host insertion; levels forced when given)
+int hnsw_host_add(annb_index *h, const float *vectors, const void *codes, const uint64_t *labels, int64_t n, int num_threads,
+                  const int32_t *forced_levels);
+// level-0 insertion on the GPU (gpu_build.cu); 1 = not applicable, take the host path
+int gpu_build_run(annb_index *h, const float *vectors, const uint64_t *labels, int64_t n, int num_threads);
 int sync_device_graph(annb_index *h);

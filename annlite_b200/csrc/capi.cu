@@ -21,11 +21,6 @@ void annb_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-enum {
-  S_QUERIES = 0, S_TABLES, S_OUT_D, S_OUT_L, S_COUNTER, S_VISITED, S_TOUCHED, S_CAND,
-  S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I,
-  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS
-};
 
 int annb_scratch(annb_index *h, int slot, size_t bytes, void **out) {
   if (bytes == 0) bytes = 16;
@@ -595,6 +590,20 @@ int annb_add_items(annb_index_t *h, const float *vectors, const void *codes, con
   if (n == 0) return ANNB_OK;
   ANNB_CUDA(cudaStreamSynchronize(h->stream));   // insertion reuses search scratch: let streamed searches finish
   ANNB_CUDA(cudaStreamSynchronize(h->stream2));
+  // num_threads == 1 is the reference's deterministic single-threaded build; any other value is an unordered
+  // concurrent build in the reference too -- large batches of fresh rows then take the GPU builder
+  if (num_threads != 1 && !codes && h->opt_gpu_build) {
+    const int rc = gpu_build_run(h, vectors, labels, n, num_threads);
+    if (rc != 1) return rc;
+  }
+  return hnsw_host_add(h, vectors, codes, labels, n, num_threads, nullptr);
+}
+
+}  // extern "C"
+
+int hnsw_host_add(annb_index *h, const float *vectors, const void *codes, const uint64_t *labels, int64_t n, int num_threads,
+                  const int32_t *forced_levels) {
+  if (n == 0) return ANNB_OK;
   const size_t crow = (size_t)h->M * h->code_bytes;
   std::vector<uint8_t> own_codes;
   const uint8_t *hc = (const uint8_t *)codes;
@@ -627,13 +636,16 @@ int annb_add_items(annb_index_t *h, const float *vectors, const void *codes, con
     ANNB_CUDA(cudaEventCreateWithFlags(&f.done[b], cudaEventDisableTiming));
     f.have_first[b] = -1;
   }
-  int rc = hnsw_insert_rows(h, hc, labels, n, num_threads, feed_next, &f, f.chunk_rows);
+  int rc = hnsw_insert_rows(h, hc, labels, n, num_threads, feed_next, &f, f.chunk_rows, forced_levels);
   cudaStreamSynchronize(h->stream);
   for (int b = 0; b < 2; b++) cudaEventDestroy(f.done[b]);
   h->dev_dirty = true;
   if (rc == ANNB_ECUDA && f.rc) return f.rc;
   return rc;
 }
+
+
+extern "C" {
 
 struct HostTables {
   const float *tables;
@@ -785,7 +797,8 @@ int sync_device_graph(annb_index *h) {
   const size_t raw_bytes = (size_t)n * g.size_per_elem;
   ANNB_TRY(annb_scratch(h, S_RAW0, raw_bytes, (void **)&raw));
   ANNB_CUDA(cudaMemcpyAsync(raw, g.level0, raw_bytes, cudaMemcpyHostToDevice, h->stream));
-  ANNB_TRY(ensure_dev((void **)&h->d_rec0, &h->cap_rec0, (size_t)n * d.rec0_bytes));
+  const int64_t n_alloc = std::max<int64_t>(n, h->reserve_nodes);  // the GPU builder appends nodes in place
+  ANNB_TRY(ensure_dev((void **)&h->d_rec0, &h->cap_rec0, (size_t)n_alloc * d.rec0_bytes));
   d.rec0 = h->d_rec0;
   ANNB_TRY(launch_pack_rec0(h, raw, n));
 
@@ -800,7 +813,7 @@ int sync_device_graph(annb_index *h) {
   }
   h->max_label = maxl;
   h->labels_identity = ident;
-  ANNB_TRY(ensure_dev((void **)&h->d_labels, &h->cap_labels, (size_t)n * 8));
+  ANNB_TRY(ensure_dev((void **)&h->d_labels, &h->cap_labels, (size_t)n_alloc * 8));
   ANNB_CUDA(cudaMemcpyAsync(h->d_labels, labels.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
   d.labels = h->d_labels;
 
@@ -1282,6 +1295,8 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "walk_kernel")) h->opt_walk_kernel = value;
   else if (!strcmp(name, "dump_tables")) h->opt_dump_tables = value;
   else if (!strcmp(name, "prefetch")) h->opt_prefetch = value;
+  else if (!strcmp(name, "gpu_build")) h->opt_gpu_build = value;
+  else if (!strcmp(name, "gpu_build_frac")) h->opt_gpu_build_frac = value;
   else if (!strcmp(name, "reset_counters")) h->flagged_fallbacks = 0;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;

@@ -668,7 +668,7 @@ struct Worker {
   }
 
   // addPoint(point, label, level=-1): hnswalg.h:1108-1235
-  int insert(const float *table, const uint8_t *code, uint64_t label) {
+  int insert(const float *table, const uint8_t *code, uint64_t label, int forced_level = -1) {
     T = table;
     uint32_t cur;
     {
@@ -692,7 +692,7 @@ struct Worker {
     // held for the whole insertion like link_list_locks_[cur_c] in the reference (:1144): until every level of
     // `cur` is linked, no other thread may append itself to one of its still-blank lists
     SpinGuard self(S.node_locks, cur, S.threaded);
-    const int curlevel = random_level();
+    const int curlevel = forced_level >= 0 ? forced_level : random_level();
     g.levels[cur] = curlevel;
 
     std::unique_lock<std::mutex> glk(S.global, std::defer_lock);
@@ -806,8 +806,17 @@ int hnsw_default_threads() {
 
 // Inserts rows [0, n) whose ADC tables are produced chunk-wise by `table_chunk(first, count)`
 // (host pointer to count*M*Ks floats valid until the next call) -- see capi.cu.
+int hnsw_draw_levels(annb_index *h, int64_t n, int32_t *out) {
+  HostGraph &g = h->g;
+  if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
+  std::uniform_real_distribution<double> distribution(0.0, 1.0);
+  for (int64_t i = 0; i < n; i++) out[i] = (int32_t)(-std::log(distribution(g.level_gen)) * g.mult);
+  return ANNB_OK;
+}
+
 int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels, int64_t n, int num_threads,
-                     const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows) {
+                     const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows,
+                     const int32_t *forced_levels) {
   HostGraph &g = h->g;
   if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph / annb_load_index first");
   int64_t fresh = 0;
@@ -846,13 +855,14 @@ int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels
     if (!tables) return ANNB_ECUDA;
     int64_t start = 0;
     if (g.count.load() == 0 && first == 0) {  // first point alone (hnsw_bindings.cpp:266-272)
-      int rc = workers[0]->insert(tables, codes, labels[0]);
+      int rc = workers[0]->insert(tables, codes, labels[0], forced_levels ? forced_levels[0] : -1);
       if (rc) return rc;
       start = 1;
     }
     if (num_threads == 1) {
       for (int64_t r = start; r < cnt; r++) {
-        int rc = workers[0]->insert(tables + (size_t)r * TS, codes + (size_t)(first + r) * crow, labels[first + r]);
+        int rc = workers[0]->insert(tables + (size_t)r * TS, codes + (size_t)(first + r) * crow, labels[first + r],
+                                    forced_levels ? forced_levels[first + r] : -1);
         if (rc) return rc;
       }
     } else {
@@ -864,7 +874,8 @@ int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels
           for (;;) {
             const int64_t r = next.fetch_add(1);
             if (r >= cnt || err.load()) break;
-            int rc = w.insert(tables + (size_t)r * TS, codes + (size_t)(first + r) * crow, labels[first + r]);
+            int rc = w.insert(tables + (size_t)r * TS, codes + (size_t)(first + r) * crow, labels[first + r],
+                              forced_levels ? forced_levels[first + r] : -1);
             if (rc) {
               std::lock_guard<std::mutex> lk(err_mu);
               if (!err.load()) {

@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
       if (pos < k) {
         const bool have = pos < size;
         p.out_dists[q * k + pos] = have ? u2f(K[e]) : CUDART_INF_F;
-        p.out_labels[q * k + pos] = have ? __ldg(g.labels + (V[e] & IDM)) : (uint64_t)UINT64_MAX;
+        p.out_labels[q * k + pos] = have ? (p.out_internal ? (uint64_t)(V[e] & IDM) : __ldg(g.labels + (V[e] & IDM))) : (uint64_t)UINT64_MAX;
       }
       const uint32_t nk = (e + 1 < EPL) ? K[e + 1 < EPL ? e + 1 : e] : k_next_lane;
       tie |= (pos + 1 < found) && (nk == K[e]) && (e + 1 < EPL || lane < 31);
