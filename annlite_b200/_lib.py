@@ -64,6 +64,7 @@ PROTOTYPES = {
     'annb_last_kernel_ms': (_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'annb_launch_count': (_int, [_vp, C.POINTER(_i64)]),
     'annb_fallback_count': (_int, [_vp, C.POINTER(_i64)]),
+    'annb_fallback_queries': (_int, [_vp, C.POINTER(_i64)]),
     'annb_set_option': (_int, [_vp, _cp, _i64]),
 }
 

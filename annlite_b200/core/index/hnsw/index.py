@@ -112,9 +112,16 @@ class HnswIndex:
         self._ensure_backend()
         if isinstance(queries, np.ndarray) or not hasattr(queries, 'data_ptr'):
             queries = self._prep(queries)
-        self._index.set_ef(max(self.ef_search, limit))
         if indices is not None and len(indices) < limit:
             limit = len(indices)
+        if limit <= 0:      # an empty candidate list: nothing can be returned (the reference would ask hnswlib for k=0)
+            B = queries.shape[0]
+            return np.empty((B, 0), dtype=np.float32), np.empty((B, 0), dtype=np.uint64)
+        from ...._lib import MAX_EF
+        if max(self.ef_search, limit) > MAX_EF:
+            raise ValueError(f'limit / ef_search above {MAX_EF} is not supported by the GPU walk (ANNB_MAX_EF); '
+                             f'use PQIndex (exhaustive scan) or lower limit={limit} / ef_search={self.ef_search}')
+        self._index.set_ef(max(self.ef_search, limit))
         if (indices is not None and self.bruteforce_filter_below is not None
                 and len(indices) <= self.bruteforce_filter_below and out_ids is None):
             ids, dists = self._index._e.scan_subset(queries, indices, k=limit, normalize=self._normalize_rounds)

@@ -130,6 +130,7 @@ struct SearchParams {
   int32_t *out_found;      // (B)
   int64_t *out_stats;      // (B,3) or nullptr
   unsigned int *work_counter;
+  const uint32_t *qmap;  // bitmap walk only: work item i -> query row (re-run of a subset; then B = #items), or nullptr
   // general-mode scratch (per warp slot)
   uint32_t *visited;      // slots * visited_words
   int64_t visited_words;
@@ -173,8 +174,8 @@ struct annb_index {
   size_t cap_rec0 = 0, cap_up = 0, cap_labels = 0, cap_deleted = 0;
 
   // scratch (grown on demand)
-  void *d_scratch[26] = {nullptr};
-  size_t scratch_cap[26] = {0};
+  void *d_scratch[28] = {nullptr};
+  size_t scratch_cap[28] = {0};
   void *h_pinned[6] = {nullptr};
   size_t pinned_cap[6] = {0};
   // asynchronous submit/wait lanes (annb_search_submit): lane i works on stream i with its own scratch
@@ -190,6 +191,7 @@ struct annb_index {
   bool labels_identity = true;     // label[i] == i for all nodes
   float last_table_ms = 0, last_search_ms = 0, last_scan_ms = 0;
   int64_t launches = 0;
+  int64_t flagged_fallback_queries = 0;  // ... and how many queries those re-runs covered
   int64_t flagged_fallbacks = 0;   // batches re-run on the bitmap walk after a flagged-list overflow
   // options
   int64_t opt_warps_per_cta = 0;   // 0 = auto
@@ -221,7 +223,7 @@ int annb_pinned(annb_index *h, int slot, size_t bytes, void **out);
 enum {
   S_QUERIES = 0, S_TABLES, S_OUT_D, S_OUT_L, S_COUNTER, S_VISITED, S_TOUCHED, S_CAND,
   S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I,
-  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS
+  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS, S_QMAP
 };
 
 // kernels (launchers)

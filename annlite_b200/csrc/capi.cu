@@ -1044,11 +1044,24 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
       if (stats_out) ANNB_CUDA(cudaMemcpyAsync(stats_out, dstats, (size_t)B * 24, cudaMemcpyDeviceToHost, h->stream));
     }
     ANNB_CUDA(cudaStreamSynchronize(h->stream));
-    bool overflowed = false;
-    for (int64_t b = 0; b < B && !overflowed; b++) overflowed = hfound[b] < 0;
-    if (!overflowed || mode == 2) break;
-    mode = 2;  // a query outgrew the flagged walk's list: redo the batch on the bitmap walk (exact, any size)
+    if (mode == 2) break;
+    // queries that outgrew the flagged walk's list (found = -1): only those are redone on the bitmap walk
+    // (exact, any size) through a query-index map; their rows of the outputs are simply overwritten
+    int64_t n_over = 0;
+    for (int64_t b = 0; b < B; b++) n_over += hfound[b] < 0;
+    if (n_over == 0) break;
+    uint32_t *hmap, *dmap;
+    ANNB_TRY(annb_pinned(h, 3, (size_t)n_over * 4, (void **)&hmap));
+    ANNB_TRY(annb_scratch(h, S_QMAP, (size_t)n_over * 4, (void **)&dmap));
+    int64_t w = 0;
+    for (int64_t b = 0; b < B; b++)
+      if (hfound[b] < 0) hmap[w++] = (uint32_t)b;
+    ANNB_CUDA(cudaMemcpyAsync(dmap, hmap, (size_t)n_over * 4, cudaMemcpyHostToDevice, h->stream));
+    p.qmap = dmap;
+    p.B = n_over;
+    mode = 2;
     h->flagged_fallbacks++;
+    h->flagged_fallback_queries += n_over;
   }
   for (int64_t b = 0; b < B; b++)
     if (hfound[b] < k)
@@ -1282,6 +1295,12 @@ int annb_fallback_count(annb_index_t *h, int64_t *out) {
   return ANNB_OK;
 }
 
+int annb_fallback_queries(annb_index_t *h, int64_t *out) {
+  if (!h || !out) ANNB_FAIL(ANNB_EINVAL, "null argument");
+  *out = h->flagged_fallback_queries;
+  return ANNB_OK;
+}
+
 int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   ANNB_ENTER(h);
   if (!name) ANNB_FAIL(ANNB_EINVAL, "null option name");
@@ -1297,7 +1316,7 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "prefetch")) h->opt_prefetch = value;
   else if (!strcmp(name, "gpu_build")) h->opt_gpu_build = value;
   else if (!strcmp(name, "gpu_build_frac")) h->opt_gpu_build_frac = value;
-  else if (!strcmp(name, "reset_counters")) h->flagged_fallbacks = 0;
+  else if (!strcmp(name, "reset_counters")) h->flagged_fallbacks = h->flagged_fallback_queries = 0;
   else ANNB_FAIL(ANNB_EINVAL, "unknown option %s", name);
   return ANNB_OK;
 }

@@ -927,8 +927,9 @@ __global__ void hnsw_walk_general(const GraphDev g, const SearchParams p, const 
   const bool use_filter = filter != nullptr;
 
   for (;;) {
-    const int64_t q = next_query(p.work_counter, lane);
-    if (q >= p.B) break;
+    const int64_t wi = next_query(p.work_counter, lane);
+    if (wi >= p.B) break;
+    const int64_t q = p.qmap ? (int64_t)__ldg(p.qmap + wi) : wi;  // subset re-run: outputs stay indexed by query row
     const float *T;
     if (SMEM_TABLE) {
       __syncwarp();
@@ -1285,40 +1286,54 @@ int launch_walk(annb_index *h, const SearchParams &p_in, bool general) {
     if (geo.smem_table) ANNB_OCC((hnsw_walk_general<EPL, CR, CB, true>));
     else ANNB_OCC((hnsw_walk_general<EPL, CR, CB, false>));
     int blocks = (int)std::min<int64_t>((int64_t)h->sm_count * occ, (p.B + geo.warps - 1) / geo.warps);
-    const int64_t slots = (int64_t)blocks * geo.warps;
+    int64_t slots = (int64_t)blocks * geo.warps;
     p.visited_words = (h->gd.n + 31) / 32;
-    p.touched_cap = 1 << 15;
-    p.cand_cap = 1 << 14;
-    uint32_t *vis;
-    static_assert(sizeof(unsigned int) == 4, "");
-    // scratch slot 5 keeps the visited bitmaps; they are left all-zero by every query, so they are
-    // cleared only when (re)allocated
-    size_t vis_bytes = (size_t)slots * p.visited_words * 4;
-    size_t before = h->scratch_cap[5];
-    if ((rc = annb_scratch(h, 5, vis_bytes, (void **)&vis))) return rc;
-    if (h->scratch_cap[5] != before) ANNB_CUDA(cudaMemsetAsync(vis, 0, h->scratch_cap[5], h->stream));
-    p.visited = vis;
-    if ((rc = annb_scratch(h, 6, (size_t)slots * p.touched_cap * 4, (void **)&p.touched))) return rc;
-    if ((rc = annb_scratch(h, 7, (size_t)slots * p.cand_cap * 8, (void **)&p.cand))) return rc;
-    if (geo.smem_table)
-      hnsw_walk_general<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del, table_stride);
-    else
-      hnsw_walk_general<EPL, CR, CB, false><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del, table_stride);
+    // per-warp scratch of the literal walk: visited log and candidate bag.  They start at sizes that cover ordinary
+    // filters and grow (x4, up to the node count: neither can hold more) when a query outgrows them -- a very
+    // selective filter or many deletions make the walk visit a large part of the graph, as the reference's does.
+    const int64_t cap_max = std::max<int64_t>(1 << 15, h->gd.n + 64);
+    int64_t tcap = 1 << 15, ccap = 1 << 14;
+    for (;;) {
+      p.touched_cap = (int)std::min<int64_t>(tcap, cap_max);
+      p.cand_cap = (int)std::min<int64_t>(ccap, cap_max);
+      // keep the per-warp scratch within ~8 GB: fewer resident warps when each needs a lot
+      while (blocks > 1 && (double)blocks * geo.warps * ((double)p.touched_cap * 4 + (double)p.cand_cap * 8) > 8e9) blocks /= 2;
+      slots = (int64_t)blocks * geo.warps;
+      uint32_t *vis;
+      static_assert(sizeof(unsigned int) == 4, "");
+      // scratch slot 5 keeps the visited bitmaps; they are left all-zero by every query, so they are
+      // cleared only when (re)allocated
+      size_t vis_bytes = (size_t)slots * p.visited_words * 4;
+      size_t before = h->scratch_cap[5];
+      if ((rc = annb_scratch(h, 5, vis_bytes, (void **)&vis))) return rc;
+      if (h->scratch_cap[5] != before) ANNB_CUDA(cudaMemsetAsync(vis, 0, h->scratch_cap[5], h->stream));
+      p.visited = vis;
+      if ((rc = annb_scratch(h, 6, (size_t)slots * p.touched_cap * 4, (void **)&p.touched))) return rc;
+      if ((rc = annb_scratch(h, 7, (size_t)slots * p.cand_cap * 8, (void **)&p.cand))) return rc;
+      ANNB_CUDA(cudaMemsetAsync(counter, 0, 8, h->stream));
+      if (geo.smem_table)
+        hnsw_walk_general<EPL, CR, CB, true><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del, table_stride);
+      else
+        hnsw_walk_general<EPL, CR, CB, false><<<blocks, threads, geo.smem_bytes, h->stream>>>(h->gd, p, has_del, table_stride);
+      h->launches++;
+      ANNB_CUDA(cudaGetLastError());
+      int32_t flag = 0;
+      ANNB_CUDA(cudaMemcpyAsync(&flag, p.overflow_flag, 4, cudaMemcpyDeviceToHost, h->stream));
+      ANNB_CUDA(cudaStreamSynchronize(h->stream));
+      if (!flag) break;
+      // visited bitmaps may be dirty after an overflow: wipe, then retry with more room
+      ANNB_CUDA(cudaMemsetAsync(h->d_scratch[5], 0, h->scratch_cap[5], h->stream));
+      if (p.touched_cap >= cap_max && p.cand_cap >= cap_max)
+        ANNB_FAIL(ANNB_ELIMIT, "general walk scratch overflow (candidate bag %d / visited log %d entries per query)", p.cand_cap,
+                  p.touched_cap);
+      tcap *= 4;
+      ccap *= 4;
+    }
+    return ANNB_OK;
   }
 #undef ANNB_OCC
   h->launches++;
   ANNB_CUDA(cudaGetLastError());
-  if (general) {
-    int32_t flag = 0;
-    ANNB_CUDA(cudaMemcpyAsync(&flag, p.overflow_flag, 4, cudaMemcpyDeviceToHost, h->stream));
-    ANNB_CUDA(cudaStreamSynchronize(h->stream));
-    if (flag) {
-      // visited bitmaps may be dirty after an overflow: wipe
-      cudaMemsetAsync(h->d_scratch[5], 0, h->scratch_cap[5], h->stream);
-      ANNB_FAIL(ANNB_ELIMIT, "general walk scratch overflow (candidate bag %d / visited log %d entries per query)",
-                p.cand_cap, p.touched_cap);
-    }
-  }
   return ANNB_OK;
 }
 

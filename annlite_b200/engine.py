@@ -311,6 +311,12 @@ class Engine:
         L.check(self._lib.annb_fallback_count(self._h, C.byref(n)))
         return n.value
 
+    @property
+    def fallback_queries(self):
+        n = C.c_int64()
+        L.check(self._lib.annb_fallback_queries(self._h, C.byref(n)))
+        return n.value
+
     def set_option(self, name, value):
         L.check(self._lib.annb_set_option(self._h, name.encode(), int(value)))
 

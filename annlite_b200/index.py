@@ -151,7 +151,9 @@ class AnnLite:
             ids = doc_ids
         offsets = np.arange(self._n, self._n + n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
         self._index.add_with_ids(x, offsets, num_threads=num_threads)
-        self._n += n
+        # `_n` is the next implicit offset: past every label handed out OR handed in (a caller-supplied id range
+        # must not be reused for later documents without ids: the graph would treat them as in-place updates)
+        self._n = max(self._n + (n if ids is None else 0), int(offsets.max()) + 1 if n else 0)
         return offsets
 
     # ---- search ---------------------------------------------------------------------------------------
@@ -272,7 +274,10 @@ class AnnLite:
         if snap is None:
             raise FileNotFoundError(f'no snapshot of parameter set {self.params_hash} under {self.data_path}')
         self._index.load(snap / 'cell_0.hnsw')
-        self._n = self._index.size
+        # labels may be sparse (caller-supplied ids): implicit offsets continue past the largest one
+        native = getattr(self._index, '_index', None)
+        ids = native.get_ids_list() if (native is not None and self._index.size) else []
+        self._n = (int(max(ids)) + 1) if len(ids) else self._index.size
 
     def close(self):
         pass

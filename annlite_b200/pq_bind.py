@@ -4,6 +4,8 @@ order and return shapes, computed by the CUDA kernels K1 / K2 through the C ABI.
 The reference functions are stateless (the codebook travels with every call); an Engine per
 (codebook buffer, metric) is cached here so repeated calls do not re-upload it.
 """
+import hashlib
+
 import numpy as np
 
 from .engine import Engine
@@ -14,7 +16,9 @@ _MAX_CACHE = 8
 
 def _engine(codebooks, ip: bool, device=0):
     cb = np.ascontiguousarray(codebooks, dtype=np.float32)
-    key = (cb.ctypes.data, cb.shape, bool(ip), device, float(cb.ravel()[:: max(1, cb.size // 64)].sum()))
+    # keyed by the codebook's CONTENT (a few hundred KB: hashing it costs microseconds): an in-place edit or a new
+    # array at a recycled address must never meet a stale copy on the GPU
+    key = (hashlib.blake2b(cb.tobytes(), digest_size=16).digest(), cb.shape, bool(ip), device)
     e = _cache.get(key)
     if e is None:
         if len(_cache) >= _MAX_CACHE:

@@ -247,6 +247,9 @@ ANNB_API int annb_last_kernel_ms(annb_index_t *h, float *table_ms, float *search
 ANNB_API int annb_launch_count(annb_index_t *h, int64_t *out);
 /* number of filtered/deleted batches that outgrew the single-list walk and were re-run on the bitmap walk */
 ANNB_API int annb_fallback_count(annb_index_t *h, int64_t *out);
+/* ... and how many queries those re-runs covered: only the queries whose list overflowed are redone (the reference's
+ * searchBaseLayerSTWithFilter, hnswalg.h:332-440, has no list to overflow) */
+ANNB_API int annb_fallback_queries(annb_index_t *h, int64_t *out);
 ANNB_API int annb_set_option(annb_index_t *h, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -65,15 +65,22 @@ def c1():
             'alg_bytes_per_query': N * M}
 
 
-def c4(n=1_000_000):
-    sys.argv = [sys.argv[0], '--metric', 'cosine', '--n', str(n)]
-    a = bench.parse()
+def c4(n=1_000_000, correlated=False):
+    """correlated=False: the filtering_bench.py shape, a random 50 % bitmap.  correlated=True: three gaussian blobs
+    (examples/pq_benchmark.py:25-28 data) and a filter that admits two WHOLE blobs (s ~ 0.67): a third of the queries
+    start inside the excluded blob and must walk out of it before they find any admissible node -- the case where
+    the flagged walk's list overflows and those queries are re-run on the bitmap walk."""
+    a = bench.parse(['--metric', 'cosine', '--n', str(n)] + (['--dist', 'blobs'] if correlated else []))
     ncores = os.cpu_count()
     cb = bench.train_codebook(a, bench.make_base(a, 0, 10_000))
     X = bench.make_base(a)
     Q = bench.make_queries(a, 1)[0]
     rng = np.random.default_rng(4)
-    allow = np.nonzero(rng.random(a.n) < 0.5)[0].astype(np.uint64)
+    if correlated:
+        blob = np.random.default_rng([2, 77]).integers(0, 3, a.n)      # the labels bench.make_base draws
+        allow = np.nonzero(blob != 2)[0].astype(np.uint64)
+    else:
+        allow = np.nonzero(rng.random(a.n) < 0.5)[0].astype(np.uint64)
     e = Engine(a.dim, a.m, a.ks, 'cosine')
     e.set_codebook(cb)
     e.init_graph(a.n, M=a.M, ef_construction=a.efc)
@@ -91,15 +98,18 @@ def c4(n=1_000_000):
     ol, od, found = O.hnsw_search(g, tq, a.k, a.ef, filter_labels=allow)
     verdict = tie_aware_rows(l[:S], d[:S], ol, od)
     rel = np.abs(d[:S] - od)[l[:S] == ol] / np.maximum(np.abs(od[l[:S] == ol]), 1e-12)
-    out = {'config': f'C4 {a.n} x 128d cosine, 50% filter bitmap ({len(allow)} ids), M=8, HNSW ef=64 k=10, {len(Q)} queries',
-           'index_build_s': t_build, 'gpu_filtered_qps_host_buffers': len(Q) / t_flt, 'gpu_filtered_kernel_ms': k_ms, 'flagged_walk_fallbacks': e.fallback_count,
+    out = {'config': f'C4 {a.n} x 128d cosine {a.dist}, {"two whole blobs admitted" if correlated else "random 50% filter bitmap"} '
+                     f'({len(allow)} ids), M=8, HNSW ef=64 k=10, {len(Q)} queries',
+           'index_build_s': t_build, 'gpu_filtered_qps_host_buffers': len(Q) / t_flt, 'gpu_filtered_kernel_ms': k_ms,
+           'flagged_walk_fallback_batches': e.fallback_count, 'flagged_walk_fallback_queries': e.fallback_queries,
+           'searches_run': 5,
            'gpu_unfiltered_qps_host_buffers': len(Q) / t_plain, 'all_results_pass_filter': bool(np.isin(l, allow).all()),
            'hops_per_query': float(st[:, 0].mean()), 'evals_per_query': float(st[:, 2].mean()),
            'parity_sample': S, 'rows_exact': verdict.count('exact'), 'rows_tie': verdict.count('tie'),
            'rows_diff': verdict.count('diff'), 'recall_vs_oracle_ids': recall(l[:S], ol),
            'max_rel_dist_err_equal_ids': float(rel.max()) if rel.size else None}
     # reference: knn_query_with_filter on its own (thread-order dependent) graph, bounded sample
-    if R.available() and n <= 1_000_000:
+    if R.available() and n <= 1_000_000 and not correlated:
         codec = R.RefCodec(cb, 'cosine')
         idx = R.RefHnswIndex(codec, 'cosine', capacity=a.n, ef_construction=a.efc, ef_search=a.ef, max_connection=a.M)
         t0 = time.time()
@@ -119,4 +129,4 @@ def c4(n=1_000_000):
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'c1'
     sys.argv = sys.argv[:1]
-    print(json.dumps(c1() if which == 'c1' else c4(int(os.environ.get('C4_N', 1_000_000)))))
+    print(json.dumps(c1() if which == 'c1' else c4(int(os.environ.get('C4_N', 1_000_000)), correlated=(which == 'c4corr'))))

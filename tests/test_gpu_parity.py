@@ -144,17 +144,24 @@ def test_k3_fused_table_build(golden):
         _check(golden, l, d, golden.knn_labels, golden.knn_dists, 8 if golden.name == 'ties_k16' else 0)
 
 
-@pytest.mark.parametrize('mode', ['auto', 'bitmap', 'tiny_list'])
+@pytest.mark.parametrize('mode', ['auto', 'bitmap', 'tiny_list', 'partial'])
 def test_k3_filtered_matches_reference(golden, mode):
     e = engine(golden)
     if mode == 'bitmap':
         e.set_option('force_general', 2)
-    if mode == 'tiny_list':          # a list too small for a 50 % filter: queries overflow and the batch is
-        e.set_option('flagged_epl', 2)                                 # re-run on the bitmap walk
+    if mode == 'tiny_list':          # a list too small for a 50 % filter: queries overflow and are re-run on
+        e.set_option('flagged_epl', 2)                                 # the bitmap walk
+    if mode == 'partial':            # 128 slots: some queries fit, some do not -- only those are re-run
+        e.set_option('flagged_epl', 4)
     t = golden.query_tables_oracle()
     l, d = e.search(tables=t, k=golden.k, ef=golden.ef, filter_labels=golden.allow)
     if mode == 'tiny_list' and golden.ef >= 50:   # 64 slots cannot hold ~2*ef candidates
         assert e.fallback_count >= 1
+    if mode in ('tiny_list', 'partial') and 32 * (2 if mode == 'tiny_list' else 4) >= golden.ef:
+        # the scalar model of the flagged walk says exactly which queries outgrow the list: only those are redone
+        *_, mf, _, _, _ = O.flagged_walk(golden.oracle_graph(), t, golden.k, golden.ef, filter_labels=golden.allow,
+                                         cap=64 if mode == 'tiny_list' else 128)
+        assert e.fallback_queries == int((mf == -1).sum())
     assert np.isin(l, golden.allow).all()
     _check(golden, l, d, golden.flt_labels, golden.flt_dists, 8 if golden.name == 'ties_k16' else 0)
 

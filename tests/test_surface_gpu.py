@@ -235,3 +235,48 @@ def test_merge_kernel_matches_host_rule():
         e.sync()
         el, ed = merge_topk_host(l, d, k)
         assert np.array_equal(ol.cpu().numpy().view(np.uint64), el) and np.array_equal(od.cpu().numpy(), ed)
+
+
+def test_annlite_explicit_then_implicit_ids_do_not_collide(tmp_path):
+    """Offsets handed out after a caller-supplied id range continue past it (an id reused would be an in-place
+    update of the earlier vector: hnswalg.h:1119-1131), also after restore() of sparse labels; an empty filter
+    returns empty rows and an oversized limit is refused with a clear message."""
+    from annlite_b200 import AnnLite
+    rng = np.random.default_rng(8)
+    D = 32
+    X = rng.standard_normal((400, D)).astype(np.float32)
+    a = AnnLite(D, metric='euclidean', n_subvectors=4, n_clusters=64, data_path=tmp_path / 'ws2', ef_search=32, initial_size=2000)
+    a.train(X, iter=5, random_state=0)
+    a.index(X[:100], ids=np.arange(100, 200))
+    off = a.index(X[100:200])
+    assert off.min() >= 200 and a.index_size == 200
+    a.dump()
+    b = AnnLite(D, metric='euclidean', n_subvectors=4, n_clusters=64, data_path=tmp_path / 'ws2', ef_search=32, initial_size=2000)
+    off2 = b.index(X[200:300])
+    assert off2.min() >= 300 and b.index_size == 300
+    d, i = b.search_numpy(X[:3], filter=np.zeros(0, dtype=np.uint64), limit=5)
+    assert d.shape == (3, 0) and i.shape == (3, 0)
+    with pytest.raises(ValueError, match='ANNB_MAX_EF'):
+        b.search_numpy(X[:3], limit=600)
+
+
+def test_general_walk_scratch_grows_for_a_very_selective_filter():
+    from annlite_b200.engine import Engine
+    """ADVICE r1: the literal (bitmap) walk must not fail when a selective filter makes it visit a large part of the
+    graph -- its per-query scratch grows instead (reference: searchBaseLayerSTWithFilter has no such limit)."""
+    rng = np.random.default_rng(9)
+    N, D, M = 120_000, 32, 8
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((16, D)).astype(np.float32)
+    cb = np.stack([X[rng.choice(N, 256, replace=False), m * 4:(m + 1) * 4] for m in range(M)]).astype(np.float32)
+    e = Engine(D, M, 256, 'euclidean')
+    e.set_codebook(cb)
+    e.init_graph(N, M=16, ef_construction=64)
+    e.add_items(X, np.arange(N, dtype=np.uint64))
+    allow = np.sort(rng.choice(N, N // 1000, replace=False)).astype(np.uint64)      # 0.1 % selectivity
+    e.set_option('force_general', 2)
+    l, d = e.search(queries=Q, k=5, ef=32, filter_labels=allow)
+    assert np.isin(l, allow).all()
+    g = O.Graph.from_state(e.get_graph(), M, 256)
+    ol, od, found = O.hnsw_search(g, O.adc_table(Q, cb), 5, 32, filter_labels=allow)
+    assert tie_aware_rows(l, d, ol, od).count('diff') == 0
