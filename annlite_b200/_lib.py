@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libannlite_b200.so')
+LIB_PATH = os.environ.get('ANNB_LIB_PATH') or os.path.join(_HERE, 'lib', 'libannlite_b200.so')   # the override is for A/B runs of kernel variants
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE, EFEWRESULTS, EIO, ECAPACITY, ENOTFOUND, ELIMIT = (
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10)

@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
       // is NOT refreshed per insertion: a candidate that the falling bound would have rejected lands at a
       // position >= ef and drops out below, exactly like the hop-start admission rule of the single-list walk ----
       if (have_new) {
+        // (A/B, round 2: checking the re-encounters of a hop four at a time ahead of the insertions, with the next
+        // candidate's key/id fetched before the current insertion, was 13 % SLOWER -- 30.4 vs 34.8 M QPS on one box:
+        // the padded groups cost more issue slots than the overlapped latencies give back at ~3.4 candidates per hop)
         unsigned live = __ballot_sync(FULL_MASK, mykey != KEY_MAX);
         while (live) {
           const int src = __ffs(live) - 1;
