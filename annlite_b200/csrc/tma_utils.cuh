@@ -34,3 +34,4 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 // L2 prefetch of one 128-byte line (no register, no scoreboard): used to warm the record of a likely next node
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
