@@ -65,6 +65,7 @@ PROTOTYPES = {
     'annb_launch_count': (_int, [_vp, C.POINTER(_i64)]),
     'annb_fallback_count': (_int, [_vp, C.POINTER(_i64)]),
     'annb_fallback_queries': (_int, [_vp, C.POINTER(_i64)]),
+    'annb_sync_counts': (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'annb_set_option': (_int, [_vp, _cp, _i64]),
 }
 

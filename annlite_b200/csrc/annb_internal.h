@@ -78,8 +78,12 @@ struct HostGraph {
   int save_file(const char *path) const;
 };
 
-// per-thread scratch + algorithm of the host builder (hnsw_build.cpp)
-struct BuildContext;
+// what a host insertion changed, for patching the device graph instead of re-deriving it (capi.cu: patch_device_graph)
+struct BuildTrack {
+  std::vector<uint32_t> dirty0;  // level-0 records rewritten (with repeats)
+  bool upper_dirty = false;      // an upper-level list, a node level > 0 or the entry point changed
+  bool untracked = false;        // an in-place update ran: no tracking, re-derive everything
+};
 
 // ------------------------------------------------------------------------------------------
 // Device graph ("walk layout"): each node's adjacency is co-located with the PQ codes of its
@@ -167,6 +171,10 @@ struct annb_index {
   HostGraph g;
   bool dev_dirty = true;
   bool deleted_dirty = false;
+  // small host insertions into a graph whose device copy was current: only the rewritten records are uploaded
+  BuildTrack patch;
+  bool patch_pending = false;
+  int64_t patches = 0, full_syncs = 0;
   GraphDev gd{};
   uint8_t *d_rec0 = nullptr, *d_up = nullptr;
   uint64_t *d_labels = nullptr;
@@ -233,6 +241,7 @@ int launch_scan(annb_index *h, const float *d_table, float *d_out);
 int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists);
 int launch_encode(annb_index *h, const float *d_x, int64_t n, void *d_codes);
 int launch_pack_rec0(annb_index *h, const uint8_t *d_level0_raw, int64_t n);
+int launch_scatter_records(annb_index *h, const uint8_t *d_staged, const uint32_t *d_ids, int64_t cnt, int rec_bytes, uint8_t *d_dst);
 // mode: 0 = fast walk (no filter, no deletions), 1 = filtered/deleted walk, kernel chosen automatically
 // (flagged single-list walk when its list fits, else the bitmap walk), 2 = bitmap walk
 int launch_search(annb_index *h, const SearchParams &p, int mode);
@@ -249,7 +258,7 @@ int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t
 // host builder
 int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels, int64_t n, int num_threads,
                      const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows,
-                     const int32_t *forced_levels = nullptr);
+                     const int32_t *forced_levels = nullptr, BuildTrack *track = nullptr);
 // the next n levels the index's generator would hand out (getRandomLevel, hnswalg.h:151-155), in order
 int hnsw_draw_levels(annb_index *h, int64_t n, int32_t *out);
 // annb_add_items without the handle lock (host insertion; levels forced when given)

@@ -636,10 +636,19 @@ int hnsw_host_add(annb_index *h, const float *vectors, const void *codes, const 
     ANNB_CUDA(cudaEventCreateWithFlags(&f.done[b], cudaEventDisableTiming));
     f.have_first[b] = -1;
   }
-  int rc = hnsw_insert_rows(h, hc, labels, n, num_threads, feed_next, &f, f.chunk_rows, forced_levels);
+  // device copy current (possibly with earlier patches pending)?  then remember what this insertion rewrites
+  const bool track = !h->dev_dirty && h->d_rec0 && h->gd.n > 0 && !forced_levels;
+  BuildTrack tr;
+  int rc = hnsw_insert_rows(h, hc, labels, n, num_threads, feed_next, &f, f.chunk_rows, forced_levels, track ? &tr : nullptr);
   cudaStreamSynchronize(h->stream);
   for (int b = 0; b < 2; b++) cudaEventDestroy(f.done[b]);
-  h->dev_dirty = true;
+  if (track && rc == ANNB_OK && !tr.untracked) {
+    h->patch.dirty0.insert(h->patch.dirty0.end(), tr.dirty0.begin(), tr.dirty0.end());
+    h->patch.upper_dirty |= tr.upper_dirty;
+    h->patch_pending = true;
+  } else {
+    h->dev_dirty = true;
+  }
   if (rc == ANNB_ECUDA && f.rc) return f.rc;
   return rc;
 }
@@ -759,14 +768,134 @@ static int upload_deleted(annb_index *h) {
   return ANNB_OK;
 }
 
+// upper levels of the walk layout + entry point, from the host graph (all of it: ~N/16 small records)
+static int upload_upper(annb_index *h) {
+  HostGraph &g = h->g;
+  GraphDev &d = h->gd;
+  const int64_t n = g.count.load();
+  d.maxlevel = g.maxlevel;
+  d.ep_node = g.enterpoint;
+  if (g.maxlevel >= ANNB_MAX_LEVELS) ANNB_FAIL(ANNB_ELIMIT, "graph has %d levels (limit %d)", g.maxlevel + 1, ANNB_MAX_LEVELS);
+  std::vector<uint8_t> up;
+  std::vector<uint32_t> map_prev, map_cur;
+  size_t off = 0;
+  for (int l = 1; l <= g.maxlevel; l++) {
+    std::vector<uint32_t> nodes;
+    for (int64_t i = 0; i < n; i++)
+      if (g.levels[i] >= l) nodes.push_back((uint32_t)i);
+    map_cur.assign((size_t)n, 0xffffffffu);
+    for (size_t r = 0; r < nodes.size(); r++) map_cur[nodes[r]] = (uint32_t)r;
+    d.up_off[l] = off;
+    up.resize(off + nodes.size() * (size_t)d.recu_bytes, 0);
+    for (size_t r = 0; r < nodes.size(); r++) {
+      uint8_t *rec = up.data() + off + r * (size_t)d.recu_bytes;
+      const uint32_t u = nodes[r];
+      const uint8_t *ll = g.list_at(u, l);
+      uint16_t cnt;
+      memcpy(&cnt, ll, 2);
+      uint32_t *links = reinterpret_cast<uint32_t *>(rec);
+      for (int j = 0; j < g.maxM; j++) {
+        uint32_t lk = 0xffffffffu;
+        if (j < (int)cnt) {
+          uint32_t v;
+          memcpy(&v, ll + 4 + 4 * j, 4);
+          if (map_cur[v] == 0xffffffffu) ANNB_FAIL(ANNB_EINVAL, "Trying to make a link on a non-existent level");
+          lk = map_cur[v];
+          memcpy(rec + d.code_offu + (size_t)j * d.code_row, g.code(v), (size_t)d.code_row);
+        }
+        links[j] = lk;
+      }
+      uint32_t tail[2] = {u, l == 1 ? u : map_prev[u]};
+      memcpy(rec + d.tail_offu, tail, 8);
+    }
+    off += nodes.size() * (size_t)d.recu_bytes;
+    if (l == g.maxlevel) d.ep_rec = map_cur[g.enterpoint];
+    map_prev.swap(map_cur);
+  }
+  if (g.maxlevel <= 0) d.ep_rec = g.enterpoint;
+  ANNB_TRY(ensure_dev((void **)&h->d_up, &h->cap_up, std::max<size_t>(up.size(), 16)));
+  if (!up.empty()) ANNB_CUDA(cudaMemcpyAsync(h->d_up, up.data(), up.size(), cudaMemcpyHostToDevice, h->stream));
+  d.up = h->d_up;
+  memcpy(d.ep_code, g.code(g.enterpoint), (size_t)d.code_row);
+  return ANNB_OK;
+}
+
+// A small host insertion into a graph whose device copy was current: upload only what changed -- the rewritten
+// level-0 records (packed on the host: links + the neighbours' codes), the new labels, and the upper levels if any
+// of them (or the entry point) moved -- instead of re-deriving all N records.
+static int patch_device_graph(annb_index *h) {
+  HostGraph &g = h->g;
+  GraphDev &d = h->gd;
+  const int64_t n = g.count.load(), n_old = d.n;
+  std::vector<uint32_t> &ids = h->patch.dirty0;
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  const size_t cnt = ids.size();
+  if (h->patch.untracked || n < n_old || cnt > (size_t)n / 4 + 64 || (size_t)n * d.rec0_bytes > h->cap_rec0 || (size_t)n * 8 > h->cap_labels) {
+    h->dev_dirty = true;   // too much changed, or the device buffers are too small: re-derive everything
+    return 1;
+  }
+  uint8_t *hst;
+  uint32_t *hid;
+  ANNB_TRY(annb_pinned(h, 0, cnt * (size_t)d.rec0_bytes + 16, (void **)&hst));
+  ANNB_TRY(annb_pinned(h, 1, cnt * 4 + 16, (void **)&hid));
+  for (size_t t = 0; t < cnt; t++) {
+    const uint32_t u = ids[t];
+    hid[t] = u;
+    uint8_t *rec = hst + t * (size_t)d.rec0_bytes;
+    memset(rec, 0, (size_t)d.rec0_bytes);
+    const uint8_t *ll = g.rec0(u);
+    uint16_t c;
+    memcpy(&c, ll, 2);
+    uint32_t *links = reinterpret_cast<uint32_t *>(rec);
+    for (int j = 0; j < g.maxM0; j++) {
+      uint32_t lk = 0xffffffffu;
+      if (j < (int)c) {
+        memcpy(&lk, ll + 4 + 4 * j, 4);
+        memcpy(rec + d.code_off0 + (size_t)j * d.code_row, g.code(lk), (size_t)d.code_row);
+      }
+      links[j] = lk;
+    }
+  }
+  uint8_t *dst;
+  uint32_t *did;
+  ANNB_TRY(annb_scratch(h, S_RAW0, cnt * (size_t)d.rec0_bytes + 16, (void **)&dst));
+  ANNB_TRY(annb_scratch(h, S_QMAP, cnt * 4 + 16, (void **)&did));
+  ANNB_CUDA(cudaMemcpyAsync(dst, hst, cnt * (size_t)d.rec0_bytes, cudaMemcpyHostToDevice, h->stream));
+  ANNB_CUDA(cudaMemcpyAsync(did, hid, cnt * 4, cudaMemcpyHostToDevice, h->stream));
+  ANNB_TRY(launch_scatter_records(h, dst, did, (int64_t)cnt, d.rec0_bytes, h->d_rec0));
+  if (n > n_old) {
+    std::vector<uint64_t> labels((size_t)(n - n_old));
+    for (int64_t i = n_old; i < n; i++) {
+      labels[i - n_old] = g.label((uint32_t)i);
+      h->max_label = std::max(h->max_label, labels[i - n_old]);
+      h->labels_identity &= labels[i - n_old] == (uint64_t)i;
+    }
+    ANNB_CUDA(cudaMemcpyAsync(h->d_labels + n_old, labels.data(), labels.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    ANNB_CUDA(cudaStreamSynchronize(h->stream));  // `labels` goes out of scope
+  }
+  d.n = n;
+  if (h->patch.upper_dirty) ANNB_TRY(upload_upper(h));
+  ANNB_CUDA(cudaStreamSynchronize(h->stream));
+  ANNB_TRY(upload_deleted(h));
+  h->patch_pending = false;
+  h->patch = BuildTrack();
+  h->patches++;
+  return ANNB_OK;
+}
+
 int sync_device_graph(annb_index *h) {
   HostGraph &g = h->g;
   if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
-  if (!h->dev_dirty && !h->deleted_dirty) return ANNB_OK;
+  if (!h->dev_dirty && !h->deleted_dirty && !h->patch_pending) return ANNB_OK;
   // device buffers are about to be rewritten / reallocated: nothing may still be walking them
   // (streamed searches of annb_search_submit run on both lanes)
   ANNB_CUDA(cudaStreamSynchronize(h->stream));
   if (h->stream2) ANNB_CUDA(cudaStreamSynchronize(h->stream2));
+  if (!h->dev_dirty && h->patch_pending) {
+    const int rc = patch_device_graph(h);
+    if (rc != 1) return rc;   // 1 = not patchable: fall through to the full re-derivation
+  }
   if (!h->dev_dirty) return upload_deleted(h);
   const int64_t n = g.count.load();
   GraphDev &d = h->gd;
@@ -817,51 +946,13 @@ int sync_device_graph(annb_index *h) {
   ANNB_CUDA(cudaMemcpyAsync(h->d_labels, labels.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
   d.labels = h->d_labels;
 
-  // upper levels
-  std::vector<uint8_t> up;
-  std::vector<uint32_t> map_prev, map_cur;
-  size_t off = 0;
-  for (int l = 1; l <= g.maxlevel; l++) {
-    std::vector<uint32_t> nodes;
-    for (int64_t i = 0; i < n; i++)
-      if (g.levels[i] >= l) nodes.push_back((uint32_t)i);
-    map_cur.assign((size_t)n, 0xffffffffu);
-    for (size_t r = 0; r < nodes.size(); r++) map_cur[nodes[r]] = (uint32_t)r;
-    d.up_off[l] = off;
-    up.resize(off + nodes.size() * (size_t)d.recu_bytes, 0);
-    for (size_t r = 0; r < nodes.size(); r++) {
-      uint8_t *rec = up.data() + off + r * (size_t)d.recu_bytes;
-      const uint32_t u = nodes[r];
-      const uint8_t *ll = g.list_at(u, l);
-      uint16_t cnt;
-      memcpy(&cnt, ll, 2);
-      uint32_t *links = reinterpret_cast<uint32_t *>(rec);
-      for (int j = 0; j < g.maxM; j++) {
-        uint32_t lk = 0xffffffffu;
-        if (j < (int)cnt) {
-          uint32_t v;
-          memcpy(&v, ll + 4 + 4 * j, 4);
-          if (map_cur[v] == 0xffffffffu) ANNB_FAIL(ANNB_EINVAL, "Trying to make a link on a non-existent level");
-          lk = map_cur[v];
-          memcpy(rec + d.code_offu + (size_t)j * d.code_row, g.code(v), (size_t)d.code_row);
-        }
-        links[j] = lk;
-      }
-      uint32_t tail[2] = {u, l == 1 ? u : map_prev[u]};
-      memcpy(rec + d.tail_offu, tail, 8);
-    }
-    off += nodes.size() * (size_t)d.recu_bytes;
-    if (l == g.maxlevel) d.ep_rec = map_cur[g.enterpoint];
-    map_prev.swap(map_cur);
-  }
-  if (g.maxlevel <= 0) d.ep_rec = g.enterpoint;
-  ANNB_TRY(ensure_dev((void **)&h->d_up, &h->cap_up, std::max<size_t>(up.size(), 16)));
-  if (!up.empty()) ANNB_CUDA(cudaMemcpyAsync(h->d_up, up.data(), up.size(), cudaMemcpyHostToDevice, h->stream));
-  d.up = h->d_up;
-  memcpy(d.ep_code, g.code(g.enterpoint), (size_t)d.code_row);
+  ANNB_TRY(upload_upper(h));
   ANNB_CUDA(cudaStreamSynchronize(h->stream));
   ANNB_TRY(upload_deleted(h));
   h->dev_dirty = false;
+  h->patch_pending = false;
+  h->patch = BuildTrack();
+  h->full_syncs++;
   return ANNB_OK;
 }
 
@@ -1157,7 +1248,7 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
   if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
   if (h->g.num_deleted > 0 || h->opt_force_general)
     ANNB_FAIL(ANNB_EINVAL, "annb_search_submit serves the plain search only (no deleted nodes / filters): use annb_search");
-  if (h->dev_dirty || h->deleted_dirty) {  // re-upload of the graph: nothing may be in flight
+  if (h->dev_dirty || h->deleted_dirty || h->patch_pending) {  // re-upload of the graph: nothing may be in flight
     ANNB_TRY(lane_wait(h, 0));
     ANNB_TRY(lane_wait(h, 1));
     ANNB_TRY(sync_device_graph(h));
@@ -1292,6 +1383,13 @@ int annb_launch_count(annb_index_t *h, int64_t *out) {
 int annb_fallback_count(annb_index_t *h, int64_t *out) {
   if (!h || !out) ANNB_FAIL(ANNB_EINVAL, "null argument");
   *out = h->flagged_fallbacks;
+  return ANNB_OK;
+}
+
+int annb_sync_counts(annb_index_t *h, int64_t *full_syncs, int64_t *patches) {
+  if (!h) ANNB_FAIL(ANNB_EINVAL, "null argument");
+  if (full_syncs) *full_syncs = h->full_syncs;
+  if (patches) *patches = h->patches;
   return ANNB_OK;
 }
 

@@ -369,6 +369,10 @@ struct Worker {
   ReHeap<std::less<Near>> h_closest;
   std::vector<Near> kept;
   std::vector<uint32_t> sel;
+  // device-graph patching: level-0 records this worker rewrote, and whether anything above level 0 (or the entry
+  // point) changed; `untracked` = an in-place update ran (updatePoint rewrites whole neighbourhoods)
+  std::vector<uint32_t> dirty0;
+  bool upper_dirty = false, untracked = false;
   const float *T = nullptr;  // ADC table of the point being inserted (n_sub x Ks)
 
   explicit Worker(SharedBuild &s) : S(s), g(*s.g) {}
@@ -493,6 +497,12 @@ struct Worker {
       top.pop();
     }
     *next_ep = sel.back();
+    if (level == 0) {
+      dirty0.push_back(cur);
+      dirty0.insert(dirty0.end(), sel.begin(), sel.end());
+    } else {
+      upper_dirty = true;
+    }
     {
       uint8_t *ll = g.list_at(cur, level);
       if (list_count(ll) && !is_update) ANNB_FAIL(ANNB_EINVAL, "The newly inserted element should have blank link list");
@@ -682,6 +692,7 @@ struct Worker {
           g.rec0(existing)[2] &= (uint8_t)~1;
           g.num_deleted--;
         }
+        untracked = true;
         return update(code, existing);
       }
       if (g.count.load() >= g.max_elements) ANNB_FAIL(ANNB_ECAPACITY, "The number of elements exceeds the specified limit");
@@ -759,6 +770,8 @@ struct Worker {
       g.enterpoint = cur;
       g.maxlevel = curlevel;
     }
+    dirty0.push_back(cur);
+    if (curlevel > 0 || (int32_t)ep_copy == -1) upper_dirty = true;
     return ANNB_OK;
   }
 };
@@ -816,7 +829,7 @@ int hnsw_draw_levels(annb_index *h, int64_t n, int32_t *out) {
 
 int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels, int64_t n, int num_threads,
                      const float *(*table_chunk)(void *, int64_t, int64_t), void *ctx, int64_t chunk_rows,
-                     const int32_t *forced_levels) {
+                     const int32_t *forced_levels, BuildTrack *track) {
   HostGraph &g = h->g;
   if (!g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph / annb_load_index first");
   int64_t fresh = 0;
@@ -892,6 +905,13 @@ int hnsw_insert_rows(annb_index *h, const uint8_t *codes, const uint64_t *labels
         annb_set_error("%s", err_msg.c_str());
         return err.load();
       }
+    }
+  }
+  if (track) {
+    for (auto &w : workers) {
+      track->dirty0.insert(track->dirty0.end(), w->dirty0.begin(), w->dirty0.end());
+      track->upper_dirty |= w->upper_dirty;
+      track->untracked |= w->untracked;
     }
   }
   return ANNB_OK;

@@ -1461,6 +1461,26 @@ int launch_pack_rec0(annb_index *h, const uint8_t *d_level0_raw, int64_t n) {
   return ANNB_OK;
 }
 
+// patch of the device graph: staged[i] (one packed record) -> dst[ids[i]]
+__global__ void scatter_records_kernel(const uint8_t *__restrict__ staged, const uint32_t *__restrict__ ids, int64_t cnt, int words,
+                                       uint8_t *__restrict__ dst) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / words;
+  if (i >= cnt) return;
+  const int w = (int)(t - i * words);
+  reinterpret_cast<uint32_t *>(dst + (size_t)ids[i] * words * 4)[w] = reinterpret_cast<const uint32_t *>(staged + (size_t)i * words * 4)[w];
+}
+
+int launch_scatter_records(annb_index *h, const uint8_t *d_staged, const uint32_t *d_ids, int64_t cnt, int rec_bytes, uint8_t *d_dst) {
+  if (cnt == 0) return ANNB_OK;
+  const int words = rec_bytes / 4;
+  const int64_t total = cnt * words;
+  scatter_records_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_staged, d_ids, cnt, words, d_dst);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
 int launch_filter_bitmap(annb_index *h, const uint64_t *d_filter_labels, int64_t n_filter, uint32_t *d_by_label,
                          uint32_t *d_by_id) {
   const int64_t n = h->gd.n;

@@ -317,6 +317,13 @@ class Engine:
         L.check(self._lib.annb_fallback_queries(self._h, C.byref(n)))
         return n.value
 
+    @property
+    def sync_counts(self):
+        """(full re-derivations of the device graph, incremental patches)"""
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self._lib.annb_sync_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_option(self, name, value):
         L.check(self._lib.annb_set_option(self._h, name.encode(), int(value)))
 

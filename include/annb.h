@@ -250,6 +250,10 @@ ANNB_API int annb_fallback_count(annb_index_t *h, int64_t *out);
 /* ... and how many queries those re-runs covered: only the queries whose list overflowed are redone (the reference's
  * searchBaseLayerSTWithFilter, hnswalg.h:332-440, has no list to overflow) */
 ANNB_API int annb_fallback_queries(annb_index_t *h, int64_t *out);
+/* How often the device copy of the graph was re-derived from the host graph in full, and how often only the records
+ * a small host insertion rewrote were uploaded (the reference searches the structure it inserts into: hnswalg.h:1108;
+ * here insertions happen on the host graph and the walk layout on the device follows). */
+ANNB_API int annb_sync_counts(annb_index_t *h, int64_t *full_syncs, int64_t *patches);
 ANNB_API int annb_set_option(annb_index_t *h, const char *name, int64_t value);
 
 #ifdef __cplusplus

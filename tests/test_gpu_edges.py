@@ -192,3 +192,53 @@ def test_hnsw_index_opt_in_bruteforce_for_selective_filters():
     da, ia = bf.search(q, limit=5, indices=many)
     db, ib = ref.search(q, limit=5, indices=many)
     assert np.array_equal(ia, ib)
+
+
+def test_small_insertions_patch_the_device_graph_instead_of_rederiving_it():
+    """Interleaved index / search (the normal AnnLite usage): after the first full derivation of the walk layout, a
+    small host insertion uploads only the level-0 records it rewrote (+ the upper levels when one of them moved);
+    every search in between must still equal the oracle on the host graph, threaded insertions and an in-place
+    update (which falls back to the full derivation) included."""
+    rng = np.random.default_rng(15)
+    N0, D, M = 30_000, 32, 8
+    X = rng.standard_normal((N0 + 4000, D)).astype(np.float32)
+    Q = rng.standard_normal((64, D)).astype(np.float32)
+    cb = np.stack([X[rng.choice(N0, 256, replace=False), m * 4:(m + 1) * 4] for m in range(M)]).astype(np.float32)
+    e = Engine(D, M, 256, 'euclidean')
+    e.set_codebook(cb)
+    e.init_graph(N0 + 4000, M=16, ef_construction=64)
+    e.add_items(X[:N0], np.arange(N0, dtype=np.uint64))
+    t = O.adc_table(Q, cb)
+
+    def check():
+        l, d = e.search(queries=Q, k=10, ef=64)
+        g = O.Graph.from_state(e.get_graph(), M, 256)
+        ol, od, found, ties = O.hnsw_search(g, t, 10, 64, with_ties=True)
+        v = np.array(tie_aware_rows(l, d, ol, od))
+        assert (v[ties == 0] == 'exact').all() and (v == 'diff').sum() <= 1
+
+    check()
+    full0, patch0 = e.sync_counts
+    done = N0
+    for step, threads in [(1, 1), (7, 1), (100, 1), (500, 4), (1000, 8), (3, 1)]:
+        e.add_items(X[done:done + step], np.arange(done, done + step, dtype=np.uint64), num_threads=threads)
+        done += step
+        check()
+    full1, patch1 = e.sync_counts
+    # six insertions, six updates of the device copy; the 1000-row one rewrites more than a quarter of this 30k-node
+    # graph's records and is allowed to re-derive everything instead
+    assert (full1 - full0) + (patch1 - patch0) == 6 and patch1 - patch0 >= 5 and full1 - full0 <= 1
+    # two insertions before one search: one patch covers both
+    e.add_items(X[done:done + 10], np.arange(done, done + 10, dtype=np.uint64), num_threads=1)
+    e.add_items(X[done + 10:done + 20], np.arange(done + 10, done + 20, dtype=np.uint64), num_threads=1)
+    done += 20
+    check()
+    assert e.sync_counts == (full1, patch1 + 1)
+    # re-adding a stored label is updatePoint: rewrites whole neighbourhoods -> full derivation, still correct
+    e.add_items(X[done:done + 1], np.array([5], dtype=np.uint64), num_threads=1)
+    check()
+    assert e.sync_counts[0] == full1 + 1
+    # deletions after a patch
+    e.mark_deleted(7)
+    l, d = e.search(queries=Q, k=10, ef=64)
+    assert not (l == 7).any()
