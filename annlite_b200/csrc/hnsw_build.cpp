@@ -709,9 +709,11 @@ struct Worker {
     std::unique_lock<std::mutex> glk(S.global, std::defer_lock);
     if (S.threaded) glk.lock();
     const int maxlevelcopy = g.maxlevel;
-    if (curlevel <= maxlevelcopy && S.threaded) glk.unlock();
+    // (the reference reads enterpoint_node_ AFTER dropping the lock, hnswalg.h:1147-1151: a benign-looking race with a
+    // thread that is installing a new top level; here level and entry point are read as one consistent pair)
     uint32_t cur_obj = g.enterpoint;
-    const uint32_t ep_copy = g.enterpoint;
+    const uint32_t ep_copy = cur_obj;
+    if (curlevel <= maxlevelcopy && S.threaded) glk.unlock();
 
     uint8_t *rec = g.rec0(cur);
     memset(rec, 0, g.size_per_elem);

@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
         e2id = __shfl_sync(FULL_MASK, myid, e2src);
         // (an L2 prefetch, not a register load: a second load into the same registers would have to wait for
         // this one to land whenever a new candidate wins)
-        if ((p.prefetch & 1) && lane * 128u < rec0_bytes) prefetch_l2(g.rec0 + (size_t)e2id * rec0_bytes + lane * 128u);
+        if (p.prefetch & 4) {         // bulk form: the TMA unit fetches the whole record on one lane's request
+          if (lane0) bulk_prefetch_l2(g.rec0 + (size_t)e2id * rec0_bytes, rec0_bytes);
+        } else if ((p.prefetch & 1) && lane * 128u < rec0_bytes) {
+          prefetch_l2(g.rec0 + (size_t)e2id * rec0_bytes + lane * 128u);
+        }
       }
       // expand that entry: flag it (the lowest matching slot of lane e2src)
       auto take_e2 = [&]() {
