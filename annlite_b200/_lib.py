@@ -57,6 +57,7 @@ PROTOTYPES = {
     'annb_search': (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _int, _vp, _int, _i64, _vp, _vp, _int, _vp]),
     'annb_scan_subset': (_int, [_vp, _vp, _int, _i64, _int, _int, _vp, _i64, _vp, _vp]),
     'annb_search_submit': (_int, [_vp, _vp, _int, _i64, _int, _int, _int, _vp, _vp, _int, C.POINTER(_int)]),
+    'annb_search_submit_filtered': (_int, [_vp, _vp, _int, _i64, _int, _int, _int, _vp, _int, _i64, _vp, _vp, _int, C.POINTER(_int)]),
     'annb_search_wait': (_int, [_vp, _int]),
     'annb_merge_topk': (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp]),
     'annb_merge_topk_packed': (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _vp, _vp, _int]),

@@ -182,8 +182,8 @@ struct annb_index {
   size_t cap_rec0 = 0, cap_up = 0, cap_labels = 0, cap_deleted = 0;
 
   // scratch (grown on demand)
-  void *d_scratch[28] = {nullptr};
-  size_t scratch_cap[28] = {0};
+  void *d_scratch[32] = {nullptr};
+  size_t scratch_cap[32] = {0};
   void *h_pinned[6] = {nullptr};
   size_t pinned_cap[6] = {0};
   // asynchronous submit/wait lanes (annb_search_submit): lane i works on stream i with its own scratch
@@ -192,6 +192,17 @@ struct annb_index {
     int64_t B = 0;
     int k = 0;
     int32_t *hfound = nullptr;
+    // what a filtered / deletion-aware batch needs to re-run its flagged queries at wait time
+    bool flagged = false;
+    int ef = 0;
+    const float *dq = nullptr;          // device queries (normalised), valid until the lane's next submit
+    const uint32_t *dfilter = nullptr;  // by-id filter bitmap or nullptr
+    float selectivity = 1.f;
+    uint64_t *dl = nullptr;
+    float *dd = nullptr;
+    int32_t *dfound = nullptr;
+    uint64_t *host_labels = nullptr;    // host outputs to refresh after a re-run, or nullptr (device outputs)
+    float *host_dists = nullptr;
   } lanes[2];
   uint32_t next_ticket = 0;
 
@@ -206,7 +217,9 @@ struct annb_index {
   int64_t opt_ctas_per_sm = 0;     // 0 = auto
   int64_t opt_force_general = 0;   // use the general (visited + candidate heap) walk always
   int64_t opt_timing = 1;
-  int64_t opt_flagged_epl = 0;     // force the flagged walk's list size (entries/32): testing the overflow fallback
+  int64_t opt_flagged_epl = 0;     // force hnsw_walk_flagged with this list size (entries/32): testing the overflow fallback
+  int64_t opt_flagged_en = 0;      // force hnsw_walk4f's traversed-only list to 32 x this many entries (2 / 4 / 8): testing
+  int64_t opt_flagged_kernel = 0;  // filtered / deleted search: 0 = hnsw_walk4f where it applies, 1 = hnsw_walk_flagged (round 1)
   int64_t opt_chunks = 0;          // host-buffer search pipeline depth: 0 = auto, 1 = off
   int64_t opt_ip_raw = 0;          // K1 IP form without the 1/Ks bias: T = 0 - ip (pq_bind compatibility)
   int64_t opt_walk_kernel = 0;     // plain search: 0 = hnsw_walk4 with fused K1 (default), 1 = round-1 kernels (K1 +
@@ -231,8 +244,10 @@ int annb_pinned(annb_index *h, int slot, size_t bytes, void **out);
 enum {
   S_QUERIES = 0, S_TABLES, S_OUT_D, S_OUT_L, S_COUNTER, S_VISITED, S_TOUCHED, S_CAND,
   S_FOUND, S_STATS, S_FLT_LABELS, S_FLT_BY_LABEL, S_FLT_BY_ID, S_RAW0, S_CODES, S_MISC, S_PART_D, S_PART_I,
-  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS, S_QMAP
+  S_L1_QUERIES, S_L1_TABLES, S_L1_OUT_D, S_L1_OUT_L, S_L1_FOUND, S_L0_FOUND, S_LANE_COUNTERS, S_QMAP,
+  S_L1_FLT_LABELS, S_L1_FLT_BY_LABEL, S_L1_FLT_BY_ID, S_SCRATCH_SLOTS
 };
+static_assert(S_SCRATCH_SLOTS <= 32, "annb_index::d_scratch is too small");
 
 // kernels (launchers)
 int launch_l2_normalize(annb_index *h, float *x, int64_t B, int D);
@@ -249,6 +264,10 @@ int launch_search(annb_index *h, const SearchParams &p, int mode);
 bool walk4_applicable(const annb_index *h);
 bool walk4_can_fuse(const annb_index *h);
 int launch_walk4(annb_index *h, const SearchParams &p);
+// hnsw_walk4f (walk_flagged4.cu): the filtered / deletion-aware search on two register lists, same table handling as
+// hnsw_walk4; returns 1 = not applicable (then hnsw_walk_flagged or the bitmap walk serve the call)
+bool walk4f_applicable(const annb_index *h, int ef, double selectivity);
+int launch_walk4f(annb_index *h, const SearchParams &p);
 // G ascending (dist, label) lists of k per query -> global k best; *_gstride = distance between two shards' arrays in elements
 int launch_merge_topk(annb_index *h, const uint64_t *labels, const float *dists, int G, int64_t B, int k, int64_t l_gstride,
                       int64_t d_gstride, uint64_t *labels_out, float *dists_out, cudaStream_t stream);

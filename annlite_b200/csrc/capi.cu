@@ -1062,9 +1062,14 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
   const float *dt = nullptr, *dq_fused = nullptr;
   const bool plain_search = !filter_labels && h->g.num_deleted == 0 && !h->opt_force_general;
+  // fraction of the nodes a filtered / deletion-aware walk can admit: sizes its lists
+  const double selectivity = filter_labels ? std::min<double>(1.0, (double)n_filter / (double)std::max<int64_t>(1, h->gd.n))
+                                           : 1.0 - (double)h->g.num_deleted / (double)std::max<int64_t>(1, h->gd.n);
+  // the table is built inside the walk for the plain search (hnsw_walk4) and for the filtered one (hnsw_walk4f)
+  const bool fuse_walk = walk4_can_fuse(h) && (plain_search || (h->opt_force_general != 2 && walk4f_applicable(h, ef_eff, selectivity)));
   if (tables) {
     ANNB_TRY(stage_in(h, tables, in_space, tbytes, S_TABLES, (const void **)&dt));
-  } else if (plain_search && walk4_can_fuse(h)) {
+  } else if (fuse_walk) {
     ANNB_TRY(stage_queries(h, queries, in_space, B, normalize, S_QUERIES, &dq_fused));
   } else {
     float *t;
@@ -1118,8 +1123,7 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   p.out_found = dfound;
   p.out_stats = dstats;
   const bool general = dfilter != nullptr || h->g.num_deleted > 0 || h->opt_force_general;
-  if (dfilter) p.selectivity = (float)std::min<double>(1.0, (double)n_filter / (double)std::max<int64_t>(1, h->gd.n));
-  else p.selectivity = (float)(1.0 - (double)h->g.num_deleted / (double)std::max<int64_t>(1, h->gd.n));
+  p.selectivity = (float)selectivity;
   int32_t *hfound;
   ANNB_TRY(annb_pinned(h, 2, (size_t)B * 4, (void **)&hfound));
   int mode = general ? (h->opt_force_general == 2 ? 2 : 1) : 0;
@@ -1148,6 +1152,13 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
     for (int64_t b = 0; b < B; b++)
       if (hfound[b] < 0) hmap[w++] = (uint32_t)b;
     ANNB_CUDA(cudaMemcpyAsync(dmap, hmap, (size_t)n_over * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!p.tables) {  // the walk built its tables in shared memory: the bitmap walk reads them from HBM (K1, all rows)
+      float *t;
+      ANNB_TRY(annb_scratch(h, S_TABLES, tbytes, (void **)&t));
+      ANNB_TRY(launch_adc_table(h, p.queries, B, t));
+      p.tables = t;
+      p.queries = nullptr;
+    }
     p.qmap = dmap;
     p.B = n_over;
     mode = 2;
@@ -1227,27 +1238,81 @@ int annb_scan_subset(annb_index_t *h, const float *queries, int in_space, int64_
 }
 
 // ---- streaming submit / wait ---------------------------------------------------------------------
+// A filtered / deletion-aware batch whose walk flagged queries (found = -1: N outgrew its capacity) is finished at
+// wait time: exactly those queries are re-run on the bitmap walk, on the lane's own stream and scratch.
+static int lane_rerun_flagged(annb_index *h, int lane, int64_t n_over) {
+  annb_index::AsyncLane &L = h->lanes[lane];
+  cudaStream_t st = lane ? h->stream2 : h->stream;
+  uint32_t *hmap, *dmap;
+  float *t;
+  ANNB_TRY(annb_pinned(h, 3, (size_t)n_over * 4, (void **)&hmap));
+  ANNB_TRY(annb_scratch(h, S_QMAP, (size_t)n_over * 4, (void **)&dmap));
+  ANNB_TRY(annb_scratch(h, lane ? S_L1_TABLES : S_TABLES, (size_t)L.B * h->M * h->Ks * sizeof(float), (void **)&t));
+  int64_t w = 0;
+  for (int64_t b = 0; b < L.B; b++)
+    if (L.hfound[b] < 0) hmap[w++] = (uint32_t)b;
+  cudaStream_t saved = h->stream;
+  h->stream = st;
+  int rc = ANNB_OK;
+  if (cudaMemcpyAsync(dmap, hmap, (size_t)n_over * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = ANNB_ECUDA;
+  if (rc == ANNB_OK) rc = launch_adc_table(h, L.dq, L.B, t);
+  if (rc == ANNB_OK) {
+    SearchParams p;
+    memset(&p, 0, sizeof(p));
+    p.tables = t;
+    p.B = n_over;
+    p.k = L.k;
+    p.ef = L.ef;
+    p.filter = L.dfilter;
+    p.selectivity = L.selectivity;
+    p.out_labels = L.dl;
+    p.out_dists = L.dd;
+    p.out_found = L.dfound;
+    p.qmap = dmap;
+    rc = launch_search(h, p, 2);
+  }
+  if (rc == ANNB_OK) {
+    cudaMemcpyAsync(L.hfound, L.dfound, (size_t)L.B * 4, cudaMemcpyDeviceToHost, st);
+    if (L.host_labels) {
+      cudaMemcpyAsync(L.host_labels, L.dl, (size_t)L.B * L.k * 8, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(L.host_dists, L.dd, (size_t)L.B * L.k * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = ANNB_ECUDA;
+  }
+  h->stream = saved;
+  if (rc == ANNB_ECUDA) annb_set_error("CUDA error while re-running flagged queries of a streamed search: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc != ANNB_OK) return rc;
+  h->flagged_fallbacks++;
+  h->flagged_fallback_queries += n_over;
+  return ANNB_OK;
+}
+
 static int lane_wait(annb_index *h, int lane) {
   annb_index::AsyncLane &L = h->lanes[lane];
   if (!L.busy) return ANNB_OK;
   cudaStream_t st = lane ? h->stream2 : h->stream;
   ANNB_CUDA(cudaStreamSynchronize(st));
   L.busy = false;
+  if (L.flagged) {
+    int64_t n_over = 0;
+    for (int64_t b = 0; b < L.B; b++) n_over += L.hfound[b] < 0;
+    if (n_over) ANNB_TRY(lane_rerun_flagged(h, lane, n_over));
+  }
   for (int64_t b = 0; b < L.B; b++)
     if (L.hfound[b] < L.k)
       ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
   return ANNB_OK;
 }
 
-int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k, int ef,
-                       uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out) {
-  ANNB_ENTER(h);
-  ANNB_NEED_GPU(h);
+// one batch, enqueued entirely on one lane: H2D -> normalise -> [filter bitmap] -> walk (tables built inside) -> D2H
+static int submit_impl(annb_index *h, const float *queries, int in_space, int64_t B, int normalize, int k, int ef,
+                       const uint64_t *filter_labels, int filter_space, int64_t n_filter, uint64_t *labels_out, float *dists_out,
+                       int out_space, int *ticket_out) {
   if (!queries || !labels_out || !dists_out || !ticket_out || B <= 0 || k <= 0 || ef <= 0) ANNB_FAIL(ANNB_EINVAL, "bad arguments");
+  if (n_filter < 0 || (n_filter > 0 && !filter_labels)) ANNB_FAIL(ANNB_EINVAL, "bad filter");
   if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
   if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
-  if (h->g.num_deleted > 0 || h->opt_force_general)
-    ANNB_FAIL(ANNB_EINVAL, "annb_search_submit serves the plain search only (no deleted nodes / filters): use annb_search");
+  if (h->opt_force_general == 2) ANNB_FAIL(ANNB_EINVAL, "streamed searches do not run on the bitmap walk: use annb_search");
   if (h->dev_dirty || h->deleted_dirty || h->patch_pending) {  // re-upload of the graph: nothing may be in flight
     ANNB_TRY(lane_wait(h, 0));
     ANNB_TRY(lane_wait(h, 1));
@@ -1256,18 +1321,25 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
   if (h->gd.n == 0) ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
   const int ef_eff = std::max(ef, k);
   if (ef_eff > ANNB_MAX_EF) ANNB_FAIL(ANNB_ELIMIT, "max(ef, k)=%d exceeds ANNB_MAX_EF=%d", ef_eff, ANNB_MAX_EF);
+  const bool general = filter_labels != nullptr || h->g.num_deleted > 0 || h->opt_force_general;
+  const double selectivity = filter_labels ? std::min<double>(1.0, (double)n_filter / (double)std::max<int64_t>(1, h->gd.n))
+                                           : 1.0 - (double)h->g.num_deleted / (double)std::max<int64_t>(1, h->gd.n);
+  const bool sparse_labels = h->max_label > (uint64_t)h->gd.n * 64 + (1ull << 30);
   const int ticket = (int)(h->next_ticket++ & 0x3fffffff);
   const int lane = ticket & 1;
   ANNB_TRY(lane_wait(h, lane));  // a lane holds one batch at a time
   const bool host_in = in_space != ANNB_DEVICE, host_out = out_space != ANNB_DEVICE;
   const size_t TS = (size_t)h->M * h->Ks;
-  const bool fuse = walk4_can_fuse(h);
+  const bool fuse = walk4_can_fuse(h) && (!general || walk4f_applicable(h, ef_eff, selectivity));
   float *dq = nullptr, *dtab = nullptr, *dd = dists_out;
   uint64_t *dl = labels_out;
   int32_t *dfound;
   unsigned int *counters;
+  uint32_t *by_id = nullptr, *by_label = nullptr;
+  uint64_t *dflt = nullptr;
   // all scratch first: a (re)allocation synchronises both lanes, which is only safe before enqueuing
-  if (host_in || normalize > 0) ANNB_TRY(annb_scratch(h, lane ? S_L1_QUERIES : S_QUERIES, (size_t)B * h->dim * sizeof(float), (void **)&dq));
+  if (host_in || normalize > 0)
+    ANNB_TRY(annb_scratch(h, lane ? S_L1_QUERIES : S_QUERIES, (size_t)B * h->dim * sizeof(float), (void **)&dq));
   if (!fuse) ANNB_TRY(annb_scratch(h, lane ? S_L1_TABLES : S_TABLES, (size_t)B * TS * sizeof(float), (void **)&dtab));
   if (host_out) {
     ANNB_TRY(annb_scratch(h, lane ? S_L1_OUT_L : S_OUT_L, (size_t)B * k * 8, (void **)&dl));
@@ -1275,6 +1347,14 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
   }
   ANNB_TRY(annb_scratch(h, lane ? S_L1_FOUND : S_L0_FOUND, (size_t)B * 4, (void **)&dfound));
   ANNB_TRY(annb_scratch(h, S_LANE_COUNTERS, 512, (void **)&counters));
+  if (filter_labels) {
+    ANNB_TRY(annb_scratch(h, lane ? S_L1_FLT_BY_ID : S_FLT_BY_ID, ((size_t)(h->gd.n + 31) / 32 + 1) * 4, (void **)&by_id));
+    if (!sparse_labels) {
+      ANNB_TRY(annb_scratch(h, lane ? S_L1_FLT_BY_LABEL : S_FLT_BY_LABEL, ((size_t)(h->max_label >> 5) + 1) * 4, (void **)&by_label));
+      if (filter_space != ANNB_DEVICE)
+        ANNB_TRY(annb_scratch(h, lane ? S_L1_FLT_LABELS : S_FLT_LABELS, (size_t)std::max<int64_t>(n_filter, 1) * 8, (void **)&dflt));
+    }
+  }
   int32_t *hfound;
   ANNB_TRY(annb_pinned(h, 4 + lane, (size_t)B * 4, (void **)&hfound));
 
@@ -1282,13 +1362,40 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
   h->stream = lane ? h->stream2 : saved;
   int rc = ANNB_OK;
   const float *src = queries;
-  if (host_in || normalize > 0) {
+  if (dq) {
     if (cudaMemcpyAsync(dq, queries, (size_t)B * h->dim * sizeof(float), host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
                         h->stream) != cudaSuccess)
       rc = ANNB_ECUDA;
     src = dq;
   }
   for (int r = 0; r < normalize && rc == ANNB_OK; r++) rc = launch_l2_normalize(h, dq, B, h->dim);
+  if (rc == ANNB_OK && filter_labels) {
+    if (sparse_labels) {
+      // labels too sparse for a by-label bitmap on the device: resolve them through the host's label -> id map
+      std::vector<uint64_t> tmp;
+      const uint64_t *hl = filter_labels;
+      if (filter_space == ANNB_DEVICE) {
+        tmp.resize((size_t)n_filter);
+        if (cudaMemcpy(tmp.data(), filter_labels, (size_t)n_filter * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = ANNB_ECUDA;
+        hl = tmp.data();
+      }
+      std::vector<uint32_t> bm((size_t)(h->gd.n + 31) / 32 + 1, 0u);
+      for (int64_t i = 0; i < n_filter && rc == ANNB_OK; i++) {
+        auto it = h->g.label_lookup.find(hl[i]);
+        if (it != h->g.label_lookup.end()) bm[it->second >> 5] |= 1u << (it->second & 31);
+      }
+      if (rc == ANNB_OK && (cudaMemcpyAsync(by_id, bm.data(), bm.size() * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+                            cudaStreamSynchronize(h->stream) != cudaSuccess))
+        rc = ANNB_ECUDA;
+    } else {
+      const uint64_t *dfl = filter_labels;
+      if (dflt) {
+        if (cudaMemcpyAsync(dflt, filter_labels, (size_t)n_filter * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = ANNB_ECUDA;
+        dfl = dflt;
+      }
+      if (rc == ANNB_OK) rc = launch_filter_bitmap(h, dfl, n_filter, by_label, by_id);
+    }
+  }
   if (rc == ANNB_OK && !fuse) rc = launch_adc_table(h, src, B, dtab);
   if (rc == ANNB_OK) {
     SearchParams p;
@@ -1298,12 +1405,13 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
     p.B = B;
     p.k = k;
     p.ef = ef_eff;
+    p.filter = by_id;
     p.out_labels = dl;
     p.out_dists = dd;
     p.out_found = dfound;
     p.work_counter = counters + 64 * lane;
-    p.selectivity = 1.f;
-    rc = launch_search(h, p, 0);
+    p.selectivity = (float)selectivity;
+    rc = launch_search(h, p, general ? 1 : 0);
   }
   if (rc == ANNB_OK) {
     cudaMemcpyAsync(hfound, dfound, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream);
@@ -1318,12 +1426,40 @@ int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int6
     if (rc == ANNB_ECUDA) annb_set_error("CUDA error while enqueuing a streamed search");
     return rc;
   }
-  h->lanes[lane].busy = true;
-  h->lanes[lane].B = B;
-  h->lanes[lane].k = k;
-  h->lanes[lane].hfound = hfound;
+  annb_index::AsyncLane &L = h->lanes[lane];
+  L.busy = true;
+  L.B = B;
+  L.k = k;
+  L.hfound = hfound;
+  L.flagged = general;
+  L.ef = ef_eff;
+  L.dq = src;
+  L.dfilter = by_id;
+  L.selectivity = (float)selectivity;
+  L.dl = dl;
+  L.dd = dd;
+  L.dfound = dfound;
+  L.host_labels = host_out ? labels_out : nullptr;
+  L.host_dists = host_out ? dists_out : nullptr;
   *ticket_out = ticket;
   return ANNB_OK;
+}
+
+int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k, int ef,
+                       uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  return submit_impl(h, queries, in_space, B, normalize, k, ef, nullptr, ANNB_HOST, 0, labels_out, dists_out, out_space, ticket_out);
+}
+
+int annb_search_submit_filtered(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k, int ef,
+                                const uint64_t *filter_labels, int filter_space, int64_t n_filter, uint64_t *labels_out,
+                                float *dists_out, int out_space, int *ticket_out) {
+  ANNB_ENTER(h);
+  ANNB_NEED_GPU(h);
+  if (!filter_labels && n_filter != 0) ANNB_FAIL(ANNB_EINVAL, "bad filter");
+  return submit_impl(h, queries, in_space, B, normalize, k, ef, filter_labels, filter_space, n_filter, labels_out, dists_out, out_space,
+                     ticket_out);
 }
 
 int annb_search_wait(annb_index_t *h, int ticket) {
@@ -1409,6 +1545,8 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "ip_raw")) h->opt_ip_raw = value;
   else if (!strcmp(name, "chunks")) h->opt_chunks = value;
   else if (!strcmp(name, "flagged_epl")) h->opt_flagged_epl = value;
+  else if (!strcmp(name, "flagged_kernel")) h->opt_flagged_kernel = value;
+  else if (!strcmp(name, "flagged_en")) h->opt_flagged_en = value;
   else if (!strcmp(name, "walk_kernel")) h->opt_walk_kernel = value;
   else if (!strcmp(name, "dump_tables")) h->opt_dump_tables = value;
   else if (!strcmp(name, "prefetch")) h->opt_prefetch = value;

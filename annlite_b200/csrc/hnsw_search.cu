@@ -1418,6 +1418,11 @@ int dispatch_flagged(annb_index *h, const SearchParams &p) {
 int launch_search(annb_index *h, const SearchParams &p, int mode) {
   if (p.B == 0) return ANNB_OK;
   if (p.B >= (int64_t)0xffffffffll) ANNB_FAIL(ANNB_ELIMIT, "at most 2^32-2 queries per call");
+  if (mode == 1) {  // filter and/or deletions: two register lists in hnsw_walk4's mapping where that applies (walk_flagged4.cu)
+    const int rc = launch_walk4f(h, p);
+    if (rc != 1) return rc;
+    if (!p.tables) ANNB_FAIL(ANNB_ESTATE, "internal: no tables for the flagged walk");
+  }
   if (mode == 1 && h->gd.maxM0 <= 32 && h->gd.n < (1ll << 30)) {
     // list capacity the flagged walk needs: every candidate down to the ef-th admitted one stays listed
     const double s = std::min(1.0, std::max(1e-4, (double)p.selectivity));

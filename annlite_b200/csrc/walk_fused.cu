@@ -34,7 +34,6 @@
 #include <math_constants.h>
 
 #include <algorithm>
-#include <type_traits>
 
 #include "annb_internal.h"
 #include "tma_utils.cuh"
@@ -64,66 +63,6 @@ constexpr int w4_max_threads(int M, int EPL) {
 constexpr int w4_min_ctas(int M, int EPL) {  // register cap = 64K / (max threads x this): must allow either residency
   const int tf = w4_ctas(M, EPL, true) * w4_cta_warps(M, EPL, true) * 32, tt = w4_ctas(M, EPL, false) * w4_cta_warps(M, EPL, false) * 32;
   return (tf > tt ? tf : tt) / w4_max_threads(M, EPL);
-}
-
-// sequential-j accumulation over one vector of coordinates; every sub / mul / add rounded on its own (no FMA)
-__device__ __forceinline__ float acc_l2(float a, const float2 w, const float2 x) {
-  float t = __fsub_rn(w.x, x.x);
-  a = __fadd_rn(a, __fmul_rn(t, t));
-  t = __fsub_rn(w.y, x.y);
-  return __fadd_rn(a, __fmul_rn(t, t));
-}
-__device__ __forceinline__ float acc_l2(float a, const float4 w, const float4 x) {
-  a = acc_l2(a, make_float2(w.x, w.y), make_float2(x.x, x.y));
-  return acc_l2(a, make_float2(w.z, w.w), make_float2(x.z, x.w));
-}
-__device__ __forceinline__ float acc_ip(float a, const float2 w, const float2 x) {
-  a = __fadd_rn(a, __fmul_rn(w.x, x.x));
-  return __fadd_rn(a, __fmul_rn(w.y, x.y));
-}
-__device__ __forceinline__ float acc_ip(float a, const float4 w, const float4 x) {
-  a = acc_ip(a, make_float2(w.x, w.y), make_float2(x.x, x.y));
-  return acc_ip(a, make_float2(w.z, w.w), make_float2(x.z, x.w));
-}
-
-// ---- K1 inside the walk: build this query's table into T (shared) ----------------------------------
-// cbt is the transposed codebook [m][j/V][c][V]; the query is staged in the tail rows of T itself (they are
-// overwritten last, after their part of the query has been consumed; the host checks that this holds).
-template <int M, int V>
-__device__ __forceinline__ void build_table(float *T, const float *__restrict__ qg, const float *__restrict__ cbt, int ds,
-                                            int is_ip, float bias, int lane) {
-  typedef typename std::conditional<V == 4, float4, float2>::type vec_t;
-  const int D = M * ds;
-  const int R = (D + 255) >> 8;
-  float *stage = T + (M - R) * 256;
-  for (int i = lane; i < D; i += 32) stage[i] = __ldg(qg + i);
-  __syncwarp();
-  const int nv = ds / V;
-  const vec_t *cb = reinterpret_cast<const vec_t *>(cbt);
-  for (int m = 0; m < M; m++) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    const vec_t *xq = reinterpret_cast<const vec_t *>(stage + m * ds);
-    const vec_t *cm = cb + (size_t)m * nv * 256 + lane;
-    if (!is_ip) {
-      for (int jv = 0; jv < nv; jv++) {
-        const vec_t x = xq[jv];
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = acc_l2(acc[i], __ldg(cm + jv * 256 + 32 * i), x);
-      }
-    } else {
-      for (int jv = 0; jv < nv; jv++) {
-        const vec_t x = xq[jv];
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = acc_ip(acc[i], __ldg(cm + jv * 256 + 32 * i), x);
-      }
-    }
-    __syncwarp();  // every lane has read q_m (and all before it): row m may now overwrite staged floats
-#pragma unroll
-    for (int i = 0; i < 8; i++) T[m * 256 + lane + 32 * i] = is_ip ? __fsub_rn(bias, acc[i]) : acc[i];
-  }
-  __syncwarp();
 }
 
 // =====================================================================================================
@@ -198,48 +137,10 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
       for (int i = lane; i < TS; i += 32) o[i] = T[i];
     }
 
-    // ---- greedy descent maxlevel..1 (hnswalg.h:1245-1274): after scanning one node's list the reference
-    // holds the FIRST minimum among the neighbours that beat curdist (strict <, sequential) ----
+    // ---- greedy descent maxlevel..1 (hnswalg.h:1245-1274), walk4_common.cuh ----
     int hops = 0, nbrs = 0, evals = 1;
-    uint32_t cur_uk;
-    {
-      float r = 0.f;
-#pragma unroll
-      for (int m = 0; m < M; m++) r = __fadd_rn(r, T[m * 256 + g.ep_code[m]]);  // dist to the entry point (:1246)
-      cur_uk = f2u(r);
-    }
-    uint32_t rec = g.ep_rec;
-    for (int level = g.maxlevel; level > 0; level--) {
-      const uint8_t *base = g.up + g.up_off[level];
-      bool changed = true;
-      while (changed) {
-        changed = false;
-        const uint8_t *r = base + (size_t)rec * g.recu_bytes;
-        hops++;
-        uint32_t link = EMPTY_LINK;
-        uint32_t cw[M / 4];
-#pragma unroll
-        for (int i = 0; i < M / 4; i++) cw[i] = 0u;
-        if (has_slotu) {
-          link = __ldg(reinterpret_cast<const uint32_t *>(r) + lane);
-          load_codes<M>(cw, r + g.code_offu + (size_t)lane * M);
-        }
-        const bool valid = link != EMPTY_LINK;
-        const uint32_t uk = valid ? f2u(pq_score<M>(T, cw)) : KEY_MAX;
-        const int nv = __popc(__ballot_sync(FULL_MASK, valid));
-        nbrs += nv;
-        evals += nv;
-        const uint32_t mn = __reduce_min_sync(FULL_MASK, uk);
-        if (mn < cur_uk) {
-          const int src = __ffs(__ballot_sync(FULL_MASK, uk == mn)) - 1;  // first index wins ties
-          rec = __shfl_sync(FULL_MASK, link, src);
-          cur_uk = mn;
-          changed = true;
-        }
-      }
-      // step down: record index on the level below (node id when level == 1)
-      rec = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)rec * g.recu_bytes + g.tail_offu) + 1);
-    }
+    uint32_t cur_uk, rec;
+    descend4<M>(g, T, lane, has_slotu, hops, nbrs, evals, cur_uk, rec);
     evals += 1;  // searchBaseLayerST re-scores the entry (:255)
 
     // ---- level 0: searchBaseLayerST as a single sorted list in registers ----

@@ -242,19 +242,31 @@ class Engine:
                                            sub.shape[0], labels.ctypes.data, dists.ctypes.data))
         return labels, dists
 
-    def search_submit(self, queries, out_labels, out_dists, k=10, ef=50, normalize=0):
+    def search_submit(self, queries, out_labels, out_dists, k=10, ef=50, normalize=0, filter_labels=None):
         """Streaming form: enqueue one batch (host numpy or device torch buffers) and return a ticket; up
-        to two batches are in flight.  The buffers must stay alive and untouched until `search_wait`."""
+        to two batches are in flight.  The buffers must stay alive and untouched until `search_wait`.
+        `filter_labels` = the allowed labels (knn_query_with_filter), host or device."""
         q = self._as_f32(queries)
         qp, qs, k0 = L.as_ptr(q)
         lp, ls, k1 = L.as_ptr(out_labels)
         dp, ds_, k2 = L.as_ptr(out_dists)
         assert ls == ds_
         t = C.c_int()
-        L.check(self._lib.annb_search_submit(self._h, qp, qs, q.shape[0], int(normalize), int(k), int(ef), lp, dp, ls,
-                                             C.byref(t)))
+        k3 = None
+        if filter_labels is None:
+            L.check(self._lib.annb_search_submit(self._h, qp, qs, q.shape[0], int(normalize), int(k), int(ef), lp, dp, ls,
+                                                 C.byref(t)))
+        else:
+            if isinstance(filter_labels, np.ndarray) or not hasattr(filter_labels, 'data_ptr'):
+                filter_labels = np.ascontiguousarray(filter_labels, dtype=np.uint64)
+            fn = int(filter_labels.shape[0])
+            if fn == 0:
+                filter_labels = np.zeros(1, dtype=np.uint64)
+            fp, fs, k3 = L.as_ptr(filter_labels)
+            L.check(self._lib.annb_search_submit_filtered(self._h, qp, qs, q.shape[0], int(normalize), int(k), int(ef), fp, fs, fn,
+                                                          lp, dp, ls, C.byref(t)))
         self._inflight = getattr(self, '_inflight', {})
-        self._inflight[t.value] = (k0, k1, k2)      # keep the buffers alive
+        self._inflight[t.value] = (k0, k1, k2, k3)      # keep the buffers alive
         self._next_ticket = t.value + 1
         return t.value
 

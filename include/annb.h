@@ -212,14 +212,22 @@ ANNB_API int annb_search(annb_index_t *h, const float *queries, const float *tab
 ANNB_API int annb_scan_subset(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k,
                      const uint64_t *subset_labels, int64_t n_subset, uint64_t *labels_out, float *dists_out);
 
-/* Streaming form of annb_search for serving loops (plain search only: no filter, no deleted nodes, no
- * stats).  annb_search_submit enqueues upload (host inputs), K1, K3 and download (host outputs) of one batch
- * on one of two internal lanes and returns a ticket at once; annb_search_wait blocks until that batch is
- * complete and reports ANNB_EFEWRESULTS like annb_search.  Two batches can be in flight, so the copies of
- * batch i+1 overlap the walk of batch i.  Buffers of a submitted batch belong to the library until its wait
- * returns; a third submit first waits for the oldest ticket of its lane. */
+/* Streaming form of annb_search for serving loops (no stats).  annb_search_submit enqueues upload (host inputs),
+ * the walk (tables built inside the kernel) and download (host outputs) of one batch on one of two internal lanes and
+ * returns a ticket at once; annb_search_wait blocks until that batch is complete and reports ANNB_EFEWRESULTS like
+ * annb_search.  Two batches can be in flight, so the copies of batch i+1 and the under-occupied tail of batch i's
+ * launch overlap.  Buffers of a submitted batch (queries, filter labels, outputs) belong to the library until its
+ * wait returns; a third submit first waits for the oldest ticket of its lane.  An index with deleted nodes is served
+ * by the deletion-aware walk (searchBaseLayerST<true>, hnswalg.h:243-329).
+ * annb_search_submit_filtered = knn_query_with_filter (bindings/hnsw_bindings.cpp:393-516) in the same form: the
+ * filter label list is uploaded and turned into the by-id bitmap on the batch's own lane; filter_labels == NULL means
+ * no filter, a non-NULL list with n_filter == 0 admits nothing.  Queries whose walk outgrew the register lists are
+ * re-run on the bitmap walk inside annb_search_wait (annb_fallback_queries counts them). */
 ANNB_API int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k,
                        int ef, uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out);
+ANNB_API int annb_search_submit_filtered(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize,
+                                int k, int ef, const uint64_t *filter_labels, int filter_space, int64_t n_filter,
+                                uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out);
 ANNB_API int annb_search_wait(annb_index_t *h, int ticket);
 
 /* ---- shard merge (CellContainer.ivf_search merge rule, annlite/container.py:130-138) ---------- */

@@ -272,3 +272,27 @@ def flagged_walk(g: Graph, tables, k, ef, filter_labels=None, cap=512):
                            C.c_uint32(g.enterpoint), g.M_sub, g.Ks, g.code_bytes, _p(tables), C.c_int64(B),
                            int(k), int(ef), _p(bm), int(cap), _p(labels), _p(dists), _p(found), _p(hops), _p(nbrs), _p(peak))
     return labels, dists, found, hops, nbrs, peak
+
+
+def two_list_walk(g: Graph, tables, k, ef, filter_labels=None, cap_n=128):
+    """NOT the reference: the scalar model of hnsw_walk4f (annlite_b200/csrc/walk_flagged4.cu), the filtered /
+    deletion-aware walk on two sorted lists (admitted / traversed only), ``orc_two_list_walk`` in pq_oracle.c.
+    Returns (labels, dists, found (-1 = the not-admitted list outgrew cap_n where it mattered), hops, nbrs, peak_n)."""
+    tables = np.ascontiguousarray(tables, dtype=np.float32)
+    B = tables.shape[0]
+    labels = np.empty((B, k), dtype=np.uint64)
+    dists = np.empty((B, k), dtype=np.float32)
+    found = np.zeros(B, dtype=np.int32)
+    hops = np.zeros(B, dtype=np.int64)
+    nbrs = np.zeros(B, dtype=np.int64)
+    peak = np.zeros(B, dtype=np.int32)
+    bm = None
+    if filter_labels is not None:
+        member = np.isin(g.labels(), np.asarray(filter_labels, dtype=np.uint64))
+        bm = np.packbits(np.concatenate([member, np.zeros(8, dtype=bool)]), bitorder='little')
+    lib().orc_two_list_walk(_p(g.level0), C.c_uint64(g.size_per_elem), C.c_uint64(g.offset_data),
+                            C.c_uint64(g.label_offset), _p(g.links), _p(g.link_off), _p(g.levels),
+                            C.c_uint64(g.size_links_per_elem), C.c_int64(g.n), C.c_int32(g.maxlevel),
+                            C.c_uint32(g.enterpoint), g.M_sub, g.Ks, g.code_bytes, _p(tables), C.c_int64(B),
+                            int(k), int(ef), _p(bm), int(cap_n), _p(labels), _p(dists), _p(found), _p(hops), _p(nbrs), _p(peak))
+    return labels, dists, found, hops, nbrs, peak

@@ -568,3 +568,150 @@ ORC_API int orc_flagged_walk(const uint8_t *level0, uint64_t size_per_elem, uint
   free(K); free(V); free(X); free(P); free(res);
   return 0;
 }
+
+/* NOT the reference's algorithm either: the scalar model of hnsw_walk4f (annlite_b200/csrc/walk_flagged4.cu), the
+ * filtered / deletion-aware walk on TWO sorted lists -- P = admitted entries (top_candidates, at most ef), N =
+ * traversed-but-not-admitted entries (candidate_set minus top_candidates, capacity cap_n) -- with the kernel's order of
+ * operations: the smallest new candidate of a hop is compared with the nearest unexpanded entry first (that decides
+ * the next node), the others follow in neighbour order; lowerBound is P's ef-th key once P is full (then N entries
+ * beyond it are dropped), else P's largest key, else FLT_MAX; an entry that falls off N's end only matters (found =
+ * -1: the host re-runs the query on the bitmap walk) while it could still have been expanded.                       */
+typedef struct { float k; uint32_t v; uint8_t x; } tl_ent;
+static int tl_listed(const tl_ent *a, int n, uint32_t id) { for (int i = 0; i < n; i++) if (a[i].v == id) return 1; return 0; }
+static void tl_insert(tl_ent *a, int *n, float key, uint32_t id, int expanded) {
+  int pos = 0;
+  while (pos < *n && a[pos].k <= key) pos++;                          /* after its equals: arrival order */
+  memmove(a + pos + 1, a + pos, sizeof(tl_ent) * (size_t)(*n - pos));
+  a[pos].k = key; a[pos].v = id; a[pos].x = (uint8_t)expanded;
+  (*n)++;
+}
+ORC_API int orc_two_list_walk(const uint8_t *level0, uint64_t size_per_elem, uint64_t offset_data,
+                              uint64_t label_offset, const uint8_t *links, const uint64_t *link_off,
+                              const int32_t *levels, uint64_t size_links_per_elem, int64_t n,
+                              int32_t maxlevel, uint32_t enterpoint, int M, int Ks, int code_bytes,
+                              const float *tables, int64_t B, int k, int ef_, const uint8_t *filter, int cap_n,
+                              uint64_t *out_labels, float *out_dists, int32_t *found, int64_t *out_hops,
+                              int64_t *out_nbrs, int32_t *out_peak_n) {
+  graph_t g = {level0, size_per_elem, offset_data, label_offset, links, link_off, levels,
+               size_links_per_elem, n, maxlevel, enterpoint, M, Ks, code_bytes};
+  if (n == 0) { for (int64_t b = 0; b < B; b++) found[b] = 0; return 0; }
+  const int ef = ef_ > k ? ef_ : k;
+  int has_del = 0;
+  for (int64_t i = 0; i < n && !has_del; i++) has_del = g_deleted(&g, (uint32_t)i);
+  const int size_guard = !filter && has_del;
+  tl_ent *P = (tl_ent *)malloc(sizeof(tl_ent) * (size_t)(ef + 80));
+  tl_ent *N = (tl_ent *)malloc(sizeof(tl_ent) * (size_t)(cap_n + 2));
+  res_t *res = (res_t *)malloc(sizeof(res_t) * (size_t)(ef + 1));
+  for (int64_t b = 0; b < B; b++) {
+    const float *t = tables + (size_t)b * M * Ks;
+    int64_t hops = 0, nbrs = 0;
+    uint32_t cur = enterpoint;
+    float curdist = pq_lookup(t, M, Ks, g_code(&g, cur), code_bytes);
+    for (int level = maxlevel; level > 0; level--) {
+      int changed = 1;
+      while (changed) {
+        changed = 0;
+        const uint8_t *ll = g_list(&g, cur, level);
+        unsigned size = g_count(ll);
+        hops++;
+        nbrs += size;
+        for (unsigned i = 0; i < size; i++) {
+          uint32_t cand = g_link(ll, i);
+          float d = pq_lookup(t, M, Ks, g_code(&g, cand), code_bytes);
+          if (d < curdist) { curdist = d; cur = cand; changed = 1; }
+        }
+      }
+    }
+#define TL_PASSES(id) (filter ? (int)((filter[(id) >> 3] >> ((id) & 7)) & 1) : !g_deleted(&g, (id)))
+    int sp = 0, sn = 0, aborted = 0, peak = 0;
+    const int ep_pass = TL_PASSES(cur);
+    if (ep_pass) tl_insert(P, &sp, curdist, cur, 1); else tl_insert(N, &sn, curdist, cur, 1);
+    float lb = ep_pass ? curdist : FLT_MAX, pmax = ep_pass ? curdist : -HUGE_VALF;
+    int have_lost = 0; float lost = 0.f;
+    uint32_t node = cur;
+    for (;;) {
+      const uint8_t *ll = g_list(&g, node, 0);
+      unsigned cnt = g_count(ll);
+      hops++;
+      nbrs += cnt;
+      const int admit_all = sp < ef;
+      const float worst = lb;
+      float ck[64]; uint32_t cid[64]; uint8_t cp[64], live[64];
+      for (unsigned j = 0; j < cnt; j++) {
+        cid[j] = g_link(ll, j);
+        ck[j] = pq_lookup(t, M, Ks, g_code(&g, cid[j]), code_bytes);
+        cp[j] = (uint8_t)TL_PASSES(cid[j]);
+        live[j] = (uint8_t)(admit_all || ck[j] < worst);               /* :306 / :413 at the hop's start */
+      }
+      /* nearest unexpanded entry of either list (P before N among equal keys) */
+      int e2l = -1, e2i = -1; float e2k = 0.f;
+      for (int i = 0; i < sp; i++) if (!P[i].x) { e2l = 0; e2i = i; e2k = P[i].k; break; }
+      for (int i = 0; i < sn; i++) if (!N[i].x) { if (e2l < 0 || N[i].k < e2k) { e2l = 1; e2i = i; e2k = N[i].k; } break; }
+      /* phase A: smallest new candidate (lower j among equals) that is not listed */
+      int have_new = 0, src = -1;
+      for (;;) {
+        src = -1;
+        for (unsigned j = 0; j < cnt; j++) if (live[j] && (src < 0 || ck[j] < ck[src])) src = (int)j;
+        if (src < 0) break;
+        live[src] = 0;
+        if (!tl_listed(P, sp, cid[src]) && !tl_listed(N, sn, cid[src])) { have_new = 1; break; }
+      }
+#define TL_INSERT(key, id, pass, expd)                                                            \
+  do {                                                                                            \
+    if (pass) { tl_insert(P, &sp, (key), (id), (expd)); if ((key) > pmax) pmax = (key);           \
+                if (sp > ef + 64) sp = ef + 64; }                                                 \
+    else {                                                                                        \
+      if (sn == cap_n) {                                                                          \
+        float lastk = N[sn - 1].k, m_ = lastk > (key) ? lastk : (key);                            \
+        if (!have_lost || m_ < lost) { lost = m_; have_lost = 1; }                                \
+      }                                                                                           \
+      tl_insert(N, &sn, (key), (id), (expd));                                                     \
+      if (sn > cap_n) sn = cap_n;                                                                 \
+    }                                                                                             \
+  } while (0)
+      float nextkey; uint32_t next;
+      if (have_new && (e2l < 0 || ck[src] < e2k)) {
+        next = cid[src]; nextkey = ck[src];
+        TL_INSERT(ck[src], cid[src], cp[src], 1);
+      } else {
+        if (e2l < 0) break;                                              /* candidate_set exhausted */
+        if (e2l == 0) { P[e2i].x = 1; next = P[e2i].v; } else { N[e2i].x = 1; next = N[e2i].v; }
+        nextkey = e2k;
+        if (have_new) TL_INSERT(ck[src], cid[src], cp[src], 0);
+      }
+      if (have_new) {
+        for (unsigned j = 0; j < cnt; j++) {
+          if (!live[j]) continue;
+          if (tl_listed(P, sp, cid[j]) || tl_listed(N, sn, cid[j])) continue;
+          TL_INSERT(ck[j], cid[j], cp[j], 0);
+        }
+        if (sn > peak) peak = sn;
+        if (sp >= ef) {
+          sp = ef;
+          lb = P[ef - 1].k;
+          int w = 0;
+          for (int i = 0; i < sn; i++) if (!(N[i].k > lb)) N[w++] = N[i];
+          sn = w;
+        } else if (sp > 0) lb = pmax;
+        if (have_lost && !(sp >= ef && lost > lb)) { aborted = 1; break; }
+      }
+      if (nextkey > lb && (!size_guard || sp >= ef)) break;              /* :371 / :270 */
+      node = next;
+    }
+#undef TL_INSERT
+#undef TL_PASSES
+    int cnt = 0;
+    if (!aborted) for (int i = 0; i < sp && i < ef && cnt < k; i++) { res[cnt].d = P[i].k; res[cnt].l = g_label(&g, P[i].v); cnt++; }
+    qsort(res, (size_t)cnt, sizeof(res_t), res_cmp);
+    for (int i = 0; i < k; i++) {
+      out_dists[(size_t)b * k + i] = i < cnt ? res[i].d : FLT_MAX;
+      out_labels[(size_t)b * k + i] = i < cnt ? res[i].l : UINT64_MAX;
+    }
+    found[b] = aborted ? -1 : cnt;
+    if (out_hops) out_hops[b] = hops;
+    if (out_nbrs) out_nbrs[b] = nbrs;
+    if (out_peak_n) out_peak_n[b] = peak;
+  }
+  free(P); free(N); free(res);
+  return 0;
+}

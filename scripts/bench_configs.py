@@ -91,6 +91,35 @@ def c4(n=1_000_000, correlated=False):
     t_flt = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow), 3)
     k_ms = e.last_kernel_ms()['search_ms']
     t_plain = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2), 3)
+    fb_batches, fb_queries = e.fallback_count, e.fallback_queries
+    # A/B: round 1's flagged walk (one list with PASS flags, shared-memory merge) on the same call
+    e.set_option('flagged_kernel', 1)
+    l1, d1 = e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow)
+    t_flt1 = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow), 3)
+    k_ms1 = e.last_kernel_ms()['search_ms']
+    e.set_option('flagged_kernel', 0)
+    same_as_round1 = tie_aware_rows(l, d, l1, d1).count('diff')
+    # streamed form (annb_search_submit_filtered): pinned host buffers, two batches in flight, the filter label list
+    # uploaded and turned into the by-id bitmap per batch on the batch's own lane
+    import torch
+    Qp = torch.from_numpy(Q).pin_memory().numpy()
+    fl = torch.from_numpy(allow.view(np.int64)).pin_memory().numpy().view(np.uint64)
+    outs = [(torch.empty((len(Q), a.k), dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+             torch.empty((len(Q), a.k), dtype=torch.float32).pin_memory().numpy()) for _ in range(2)]
+
+    def streamed(nb):
+        tk = []
+        t0 = time.perf_counter()
+        for i in range(nb):
+            if i >= 2:
+                e.search_wait(tk[i - 2])
+            tk.append(e.search_submit(Qp, outs[i & 1][0], outs[i & 1][1], k=a.k, ef=a.ef, normalize=2, filter_labels=fl))
+        e.search_wait(tk[-2])
+        e.search_wait(tk[-1])
+        return (time.perf_counter() - t0) / nb
+    streamed(4)
+    t_str = min(streamed(20) for _ in range(3)) if not correlated else streamed(4)
+    streamed_same = bool(np.array_equal(outs[1][0], l) and np.array_equal(outs[1][1], d))
     # parity on the same graph: oracle port (filter semantic), bounded sample
     S = 2000
     g = O.Graph.from_state(e.get_graph(), a.m, a.ks)
@@ -101,15 +130,20 @@ def c4(n=1_000_000, correlated=False):
     out = {'config': f'C4 {a.n} x 128d cosine {a.dist}, {"two whole blobs admitted" if correlated else "random 50% filter bitmap"} '
                      f'({len(allow)} ids), M=8, HNSW ef=64 k=10, {len(Q)} queries',
            'index_build_s': t_build, 'gpu_filtered_qps_host_buffers': len(Q) / t_flt, 'gpu_filtered_kernel_ms': k_ms,
-           'flagged_walk_fallback_batches': e.fallback_count, 'flagged_walk_fallback_queries': e.fallback_queries,
+           'flagged_walk_fallback_batches': fb_batches, 'flagged_walk_fallback_queries': fb_queries,
            'searches_run': 5,
+           'filtered_kernel': 'hnsw_walk4f (two register lists, table built in shared memory)',
+           'gpu_filtered_qps_streamed_host_buffers': len(Q) / t_str, 'streamed_ms_per_batch': t_str * 1e3,
+           'streamed_rows_equal_blocking_call': streamed_same,
+           'round1_flagged_walk': {'gpu_filtered_qps_host_buffers': len(Q) / t_flt1, 'kernel_ms_excl_table_kernel': k_ms1,
+                                   'rows_diff_vs_new_kernel': same_as_round1},
            'gpu_unfiltered_qps_host_buffers': len(Q) / t_plain, 'all_results_pass_filter': bool(np.isin(l, allow).all()),
            'hops_per_query': float(st[:, 0].mean()), 'evals_per_query': float(st[:, 2].mean()),
            'parity_sample': S, 'rows_exact': verdict.count('exact'), 'rows_tie': verdict.count('tie'),
            'rows_diff': verdict.count('diff'), 'recall_vs_oracle_ids': recall(l[:S], ol),
            'max_rel_dist_err_equal_ids': float(rel.max()) if rel.size else None}
     # reference: knn_query_with_filter on its own (thread-order dependent) graph, bounded sample
-    if R.available() and n <= 1_000_000 and not correlated:
+    if R.available() and n <= 1_000_000 and not correlated and not os.environ.get('C4_SKIP_REF'):
         codec = R.RefCodec(cb, 'cosine')
         idx = R.RefHnswIndex(codec, 'cosine', capacity=a.n, ef_construction=a.efc, ef_search=a.ef, max_connection=a.M)
         t0 = time.time()

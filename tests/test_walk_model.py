@@ -222,3 +222,65 @@ def test_flagged_model_capacity_rule_and_overflow_flag():
     allow = labels[rng.random(g.n) < 0.3]
     ml, md, mf, mh, mn, peak = O.flagged_walk(g, t, 10, 64, filter_labels=allow, cap=128)   # needs ~ 64/0.3 = 213 entries
     assert (mf == -1).mean() > 0.9
+
+
+# ---- two-list walk (hnsw_walk4f: admitted list P + traversed-only list N): scalar C model vs the oracle ----------
+@pytest.mark.parametrize('mode', ['filter', 'deleted', 'plain'])
+def test_two_list_model_vs_oracle_on_fixtures(golden, mode):
+    from helpers import tie_aware_rows
+    g = golden.oracle_graph(deleted=(mode == 'deleted'))
+    fl = golden.allow if mode == 'filter' else None
+    t = golden.query_tables_oracle()
+    ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t, golden.k, golden.ef, filter_labels=fl, with_counts=True, with_ties=True)
+    ml, md, mf, mh, mn, peak = O.two_list_walk(g, t, golden.k, golden.ef, filter_labels=fl, cap_n=256)
+    assert np.array_equal(mf, found)
+    v = np.array(tie_aware_rows(ml, md, ol, od))
+    clean = ties == 0
+    assert (v[clean] == 'exact').all()
+    assert np.array_equal(mh[clean], hops[clean]) and np.array_equal(mn[clean], nbrs[clean])
+    assert (v[~clean] == 'diff').sum() <= (3 if golden.name == 'ties_k16' else 0)
+
+
+def walk4f_en_for(ef, s):
+    """launch_walk4f's capacity rule for the traversed-only list (walk_flagged4.cu: walk4f_en_for)."""
+    s = min(1.0, max(1e-4, s))
+    need = ef * (1 - s) / s + 5.0 * np.sqrt(ef * (1 - s)) / s + 16.0
+    return next((en for en in (2, 4, 8) if en * 32 >= need), 0)
+
+
+def test_two_list_model_capacity_rule_and_overflow_flag():
+    """N's capacity rule against the peak size N reaches under random filters; a query is flagged (found = -1) only
+    when an entry that could still be expanded fell off N -- every unflagged row is the oracle's."""
+    from helpers import tie_aware_rows
+    g, t = _host_built(20000, 64, 8, 256, 21, threads=8)
+    rng = np.random.default_rng(4)
+    labels = g.labels()
+    for ef, s in ((64, 0.9), (64, 0.5), (64, 0.4), (128, 0.5), (10, 0.5), (100, 0.7)):
+        allow = labels[rng.random(g.n) < s]
+        en = walk4f_en_for(ef, len(allow) / g.n)
+        assert en > 0
+        ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t, 10, ef, filter_labels=allow, with_counts=True, with_ties=True)
+        ml, md, mf, mh, mn, peak = O.two_list_walk(g, t, 10, ef, filter_labels=allow, cap_n=32 * en)
+        assert (mf == found).all(), (ef, s, int((mf == -1).sum()), int(peak.max()))     # no query overflows under a random filter
+        v = np.array(tie_aware_rows(ml, md, ol, od))
+        clean = ties == 0
+        assert (v[clean] == 'exact').all() and np.array_equal(mh[clean], hops[clean]) and np.array_equal(mn[clean], nbrs[clean])
+        assert (v[~clean] == 'diff').sum() <= 1
+    # a capacity that is too small on purpose: flagged rows are re-run by the host, the others must still be right
+    allow = labels[rng.random(g.n) < 0.3]
+    ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t, 10, 64, filter_labels=allow, with_counts=True, with_ties=True)
+    for cap in (64, 128, 160):
+        ml, md, mf, mh, mn, peak = O.two_list_walk(g, t, 10, 64, filter_labels=allow, cap_n=cap)
+        ok = mf >= 0
+        v = np.array(tie_aware_rows(ml[ok], md[ok], ol[ok], od[ok]))
+        clean = ties[ok] == 0
+        assert (v[clean] == 'exact').all() and np.array_equal(mh[ok][clean], hops[ok][clean])
+        if cap == 64:
+            assert (mf == -1).mean() > 0.9       # needs ~ 64 * 0.7 / 0.3 = 150 entries
+    # deletions: every tenth node deleted (N stays tiny), and a filter that admits nothing near the entry point
+    st_labels = labels[rng.random(g.n) < 0.02]
+    ol, od, found, (hops, nbrs, _), ties = O.hnsw_search(g, t[:64], 5, 16, filter_labels=st_labels, with_counts=True, with_ties=True)
+    ml, md, mf, mh, mn, peak = O.two_list_walk(g, t[:64], 5, 16, filter_labels=st_labels, cap_n=100000)
+    assert np.array_equal(mf, found)
+    v = np.array(tie_aware_rows(ml, md, ol, od))
+    assert (v[ties == 0] == 'exact').all() and np.array_equal(mh[ties == 0], hops[ties == 0])
