@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
       // ---- score the neighbour list: one lane = one neighbour, m sequential ----
       const uint32_t uk = f2u(pq_score<M>(T, cur.cw));
       uint32_t mykey = (valid && uk < worst) ? uk : KEY_MAX;
-      const unsigned passmask = __ballot_sync(FULL_MASK, pf != 0u);
       if (stats) {
         const int nv = __popc(__ballot_sync(FULL_MASK, valid));
         nbrs += nv;
@@ -271,18 +270,13 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
           break;
         }
       }
-      uint32_t nextkey;
-      if (have_new && mn < e2key) {
-        load_rec(nxt, id);
-        insert(mn, id | EXP_BIT, (passmask >> src) & 1u);
-        nextkey = mn;
-      } else {
-        if (e2key == KEY_MAX) return false;  // candidate_set exhausted (:266 / :367)
-        load_rec(nxt, e2id);
-        take_e2();
-        if (have_new) insert(mn, id, (passmask >> src) & 1u);
-        nextkey = e2key;
-      }
+      const bool new_is_next = have_new && mn < e2key;
+      if (!new_is_next && e2key == KEY_MAX) return false;  // candidate_set exhausted (:266 / :367)
+      load_rec(nxt, new_is_next ? id : e2id);  // requested BEFORE the admission bits are waited for: the two round trips overlap
+      if (!new_is_next) take_e2();
+      const uint32_t nextkey = new_is_next ? mn : e2key;
+      const unsigned passmask = __ballot_sync(FULL_MASK, pf != 0u);
+      if (have_new) insert(mn, new_is_next ? (id | EXP_BIT) : id, (passmask >> src) & 1u);
       // ---- phase B: the other admitted candidates in lane order ----
       if (have_new) {
         unsigned live = __ballot_sync(FULL_MASK, mykey != KEY_MAX);

@@ -92,6 +92,11 @@ def c4(n=1_000_000, correlated=False):
     k_ms = e.last_kernel_ms()['search_ms']
     t_plain = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2), 3)
     fb_batches, fb_queries = e.fallback_count, e.fallback_queries
+    e.set_option('chunks', 1)                                      # one launch: the plain walk's kernel time on the same index
+    _, _, st_plain = e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, with_stats=True)
+    e.search(queries=Q, k=a.k, ef=a.ef, normalize=2)
+    k_ms_plain = e.last_kernel_ms()['search_ms']
+    e.set_option('chunks', 0)
     # A/B: round 1's flagged walk (one list with PASS flags, shared-memory merge) on the same call
     e.set_option('flagged_kernel', 1)
     l1, d1 = e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow)
@@ -137,7 +142,8 @@ def c4(n=1_000_000, correlated=False):
            'streamed_rows_equal_blocking_call': streamed_same,
            'round1_flagged_walk': {'gpu_filtered_qps_host_buffers': len(Q) / t_flt1, 'kernel_ms_excl_table_kernel': k_ms1,
                                    'rows_diff_vs_new_kernel': same_as_round1},
-           'gpu_unfiltered_qps_host_buffers': len(Q) / t_plain, 'all_results_pass_filter': bool(np.isin(l, allow).all()),
+           'gpu_unfiltered_qps_host_buffers': len(Q) / t_plain, 'unfiltered_kernel_ms': k_ms_plain,
+           'unfiltered_hops_per_query': float(st_plain[:, 0].mean()), 'all_results_pass_filter': bool(np.isin(l, allow).all()),
            'hops_per_query': float(st[:, 0].mean()), 'evals_per_query': float(st[:, 2].mean()),
            'parity_sample': S, 'rows_exact': verdict.count('exact'), 'rows_tie': verdict.count('tie'),
            'rows_diff': verdict.count('diff'), 'recall_vs_oracle_ids': recall(l[:S], ol),

@@ -56,6 +56,7 @@ def test_filtered_walk_matches_the_oracle(D, M, k, ef, s):
     g = O.Graph.from_state(e.get_graph(), M, 256)
     t = O.adc_table(Q, cb, 'euclidean')
     allow = labels[rng.random(N) < s]
+    e.search(queries=Q[:4], k=k, ef=ef)                             # the first search after an insertion syncs the device graph
     n0 = e.launch_count
     l, d, st = e.search(queries=Q, k=k, ef=ef, filter_labels=allow, with_stats=True)        # fused table build
     assert e.launch_count - n0 == 3 and e.fallback_count == 0      # bitmap (2 kernels) + ONE walk kernel, no K1
