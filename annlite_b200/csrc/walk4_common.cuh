@@ -95,6 +95,20 @@ __device__ __forceinline__ void list_insert(uint32_t (&K)[EPL], uint32_t (&V)[EP
   }
 }
 
+// nearest not-yet-expanded entry of one lane's slots, as a running (key, value) minimum: expanded and empty slots
+// count as KEY_MAX (their flag bit smeared over the key); strict < keeps the lowest slot among equal keys
+template <int EPL>
+__device__ __forceinline__ void unexpanded_min(const uint32_t (&K)[EPL], const uint32_t (&V)[EPL], uint32_t &bk, uint32_t &bv) {
+#pragma unroll
+  for (int e = 0; e < EPL; e++) {
+    const uint32_t c = K[e] | (uint32_t)((int32_t)V[e] >> 31);
+    if (c < bk) {
+      bk = c;
+      bv = V[e];
+    }
+  }
+}
+
 template <int EPL>
 __device__ __forceinline__ uint32_t list_key_at(const uint32_t (&K)[EPL], int lane_of, int slot_of) {
   uint32_t sel = K[0];

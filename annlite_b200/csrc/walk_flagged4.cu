@@ -16,16 +16,22 @@
 //   N  the traversed-but-not-admitted entries = the members of candidate_set that are not in top_candidates.
 // An insertion goes to ONE of them (the pass bit of the candidate is warp-uniform), so it costs what it costs in the
 // plain search.  lowerBound (top_candidates.top()) is P's ef-th key once P is full, else P's largest key, else
-// FLT_MAX (:256-260 / :353-360); once P is full, N entries beyond lowerBound are dropped (they are never expanded:
-// the loop breaks first, :270 / :371), while P is not full nothing is dropped -- which is what makes the walk exact
-// without a visited set (a re-encountered node is still listed, or was dropped with d > a lowerBound that has only
-// fallen since).  The next node is the nearest unexpanded entry of either list or a closer new candidate; the
-// break rules are the reference's: with a filter `d > lowerBound` alone (:371, no size guard), with deletions
-// `d > lowerBound && (size == ef || !has_deletions)` (:270).
+// FLT_MAX (:256-260 / :353-360).  N entries beyond lowerBound are never expanded (the loop breaks first, :270 / :371);
+// they are not pruned either -- N simply keeps its 32*EN smallest entries, so what falls off its end when it is full
+// are those dead entries first.  While P is not full nothing may be lost -- which is what makes the walk exact
+// without a visited set (a re-encountered node is still listed, or was lost with d > a lowerBound that has only
+// fallen since and fails the admission test).  The next node is the nearest unexpanded entry of either list or a
+// closer new candidate; the break rules are the reference's: with a filter `d > lowerBound` alone (:371, no size
+// guard), with deletions `d > lowerBound && (size == ef || !has_deletions)` (:270).
 //
-// N has a fixed capacity (32*EN, chosen by the host from the selectivity).  Lane 31 tracks the smallest key that ever
-// fell off N's end; the query is flagged (found = -1) only if such an entry could still have mattered (P not full, or
-// its key <= lowerBound) and the host re-runs exactly those queries on the bitmap walk.
+// N's capacity (32*EN) is chosen by the host from the selectivity.  Lane 31 tracks the smallest key that ever fell off
+// N's end; the query is flagged (found = -1) only if such an entry could still have mattered (P not full, or its key
+// <= lowerBound) and the host re-runs exactly those queries on the bitmap walk.
+//
+// Instruction diet (ncu, first version: 435 warp instructions per hop, ALU pipe 83 % busy): the nearest unexpanded
+// entry is tracked as a per-lane (key, value) minimum and flagged by id (was: key scan + slot search + flag search,
+// 13 instructions per slot); the re-encounter check compares KEYS first and ids only when a key matches; N is not
+// pruned per hop.
 //
 // Differences from the reference are confined to exact fp32 ties (arrival order instead of heap order), as for
 // every single-list walk here; tests/test_gpu_walk4.py checks ids, distance bits, hop and neighbour counts against
@@ -186,43 +192,26 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
       uint32_t pf = 0u;
       if (valid) pf = passes(cur.link);
 
-      // ---- nearest not-yet-expanded entry of either list == candidate_set.top() (:268 / :369) ----
-      uint32_t lm = KEY_MAX;
-#pragma unroll
-      for (int e = 0; e < EP; e++) lm = min(lm, KP[e] | (uint32_t)((int32_t)VP[e] >> 31));
-#pragma unroll
-      for (int e = 0; e < EN; e++) lm = min(lm, KN[e] | (uint32_t)((int32_t)VN[e] >> 31));
+      // ---- nearest not-yet-expanded entry of either list == candidate_set.top() (:268 / :369): every lane keeps
+      // the (key, value) of its own nearest one (lowest slot among equals, P before N), one REDUX picks the lane ----
+      uint32_t lm = KEY_MAX, lv = 0u;
+      unexpanded_min<EP>(KP, VP, lm, lv);
+      unexpanded_min<EN>(KN, VN, lm, lv);
       const uint32_t e2key = __reduce_min_sync(FULL_MASK, lm);
-      int e2src = 0;
       uint32_t e2id = 0;
       if (e2key != KEY_MAX) {
-        e2src = __ffs(__ballot_sync(FULL_MASK, lm == e2key)) - 1;
-        uint32_t myid = 0;
-#pragma unroll
-        for (int e = EN - 1; e >= 0; e--)
-          if ((KN[e] | (uint32_t)((int32_t)VN[e] >> 31)) == e2key) myid = VN[e] & IDM;
-#pragma unroll
-        for (int e = EP - 1; e >= 0; e--)
-          if ((KP[e] | (uint32_t)((int32_t)VP[e] >> 31)) == e2key) myid = VP[e] & IDM;  // lowest slot, P before N
-        e2id = __shfl_sync(FULL_MASK, myid, e2src);
+        const int e2src = __ffs(__ballot_sync(FULL_MASK, lm == e2key)) - 1;
+        e2id = __shfl_sync(FULL_MASK, lv, e2src);  // (an unexpanded entry's value is its node id: no flag bit set)
         if ((p.prefetch & 1) && lane * 128u < rec0_bytes) prefetch_l2(g.rec0 + (size_t)e2id * rec0_bytes + lane * 128u);
       }
+      // expand that entry: ids are unique in the lists and an unexpanded entry's value IS its id
       auto take_e2 = [&]() {
-        if (lane == e2src) {
-          bool done = false;
 #pragma unroll
-          for (int e = 0; e < EP; e++) {
-            const bool hit = !done && (KP[e] | (uint32_t)((int32_t)VP[e] >> 31)) == e2key;
-            if (hit) VP[e] |= EXP_BIT;
-            done |= hit;
-          }
+        for (int e = 0; e < EP; e++)
+          if (VP[e] == e2id) VP[e] |= EXP_BIT;
 #pragma unroll
-          for (int e = 0; e < EN; e++) {
-            const bool hit = !done && (KN[e] | (uint32_t)((int32_t)VN[e] >> 31)) == e2key;
-            if (hit) VN[e] |= EXP_BIT;
-            done |= hit;
-          }
-        }
+        for (int e = 0; e < EN; e++)
+          if (VN[e] == e2id) VN[e] |= EXP_BIT;
       };
 
       // ---- score the neighbour list: one lane = one neighbour, m sequential ----
@@ -234,7 +223,15 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
         evals += nv;
       }
 
-      auto listed = [&](uint32_t id) -> bool {
+      // re-encounter of a listed node?  An id can only be listed under this very key, so the id compare runs only
+      // when some entry has an equal key (a re-encounter, or an exact fp32 tie between two nodes)
+      auto listed = [&](uint32_t key, uint32_t id) -> bool {
+        bool eq = false;
+#pragma unroll
+        for (int e = 0; e < EP; e++) eq |= KP[e] == key;
+#pragma unroll
+        for (int e = 0; e < EN; e++) eq |= KN[e] == key;
+        if (!__any_sync(FULL_MASK, eq)) return false;
         bool dup = false;
 #pragma unroll
         for (int e = 0; e < EP; e++) dup |= (VP[e] & IDM) == id;
@@ -265,7 +262,7 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
         src = __ffs(__ballot_sync(FULL_MASK, mykey == mn)) - 1;
         id = __shfl_sync(FULL_MASK, cur.link, src);
         if (lane == src) mykey = KEY_MAX;
-        if (!listed(id)) {
+        if (!listed(mn, id)) {
           have_new = true;
           break;
         }
@@ -285,10 +282,10 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
           live &= live - 1;
           const uint32_t ck = __shfl_sync(FULL_MASK, mykey, s2);
           const uint32_t cid = __shfl_sync(FULL_MASK, cur.link, s2);
-          if (listed(cid)) continue;
+          if (listed(ck, cid)) continue;
           insert(ck, cid, (passmask >> s2) & 1u);
         }
-        // ---- lowerBound = top_candidates.top() (:320-321 / :429-430); drop what lies beyond it ----
+        // ---- lowerBound = top_candidates.top() (:320-321 / :429-430) ----
         if (sizeP >= ef) {
           sizeP = ef;
           lb = list_key_at<EP>(KP, wl, ws);
@@ -301,12 +298,8 @@ __global__ void __launch_bounds__(w4f_max_threads(M, EP, EN), w4f_min_ctas(M, EP
                 VP[e] = 0xffffffffu;
               }
           }
-#pragma unroll
-          for (int e = 0; e < EN; e++)
-            if (KN[e] > lb) {
-              KN[e] = KEY_MAX;
-              VN[e] = 0xffffffffu;
-            }
+          // (N is not pruned: entries beyond lowerBound are never expanded -- the break rule below ends the walk
+          // before -- and they are the first to fall off N's end when it is full)
         } else if (sizeP > 0) {
           lb = pmax;
         }
@@ -423,13 +416,13 @@ int launch_walk4f_m(annb_index *h, const SearchParams &p, int ep, int en) {
 }  // namespace
 
 // N's capacity for a filter (or deletion rate) that admits a fraction s of the nodes.  While P holds fewer than ef
-// entries N keeps every rejected node that was evaluated: a negative-binomial count with mean ef(1-s)/s and variance
-// ef(1-s)/s^2; afterwards it keeps the rejected nodes below lowerBound, the same count again.  5 sigma + one hop's
-// worth of arrivals on top of the mean; a query that needs more is flagged and re-run on the bitmap walk.
+// entries N must keep every rejected node that was evaluated: a negative-binomial count with mean ef(1-s)/s and
+// variance ef(1-s)/s^2; afterwards it must keep the rejected nodes below lowerBound, the same count again.  Mean +
+// 4.5 sigma (one query in ~3e5 needs more; it is flagged and re-run on the bitmap walk).
 static int walk4f_en_for(int ef, double s) {
   s = std::min(1.0, std::max(1e-4, s));
   const double mean = ef * (1.0 - s) / s, sd = std::sqrt(ef * (1.0 - s)) / s;
-  const double need = mean + 5.0 * sd + 16.0;
+  const double need = mean + 4.5 * sd + 4.0;
   for (int en : {2, 4, 8})
     if (en * 32 >= need) return en;
   return 0;

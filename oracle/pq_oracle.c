@@ -573,9 +573,10 @@ ORC_API int orc_flagged_walk(const uint8_t *level0, uint64_t size_per_elem, uint
  * filtered / deletion-aware walk on TWO sorted lists -- P = admitted entries (top_candidates, at most ef), N =
  * traversed-but-not-admitted entries (candidate_set minus top_candidates, capacity cap_n) -- with the kernel's order of
  * operations: the smallest new candidate of a hop is compared with the nearest unexpanded entry first (that decides
- * the next node), the others follow in neighbour order; lowerBound is P's ef-th key once P is full (then N entries
- * beyond it are dropped), else P's largest key, else FLT_MAX; an entry that falls off N's end only matters (found =
- * -1: the host re-runs the query on the bitmap walk) while it could still have been expanded.                       */
+ * the next node), the others follow in neighbour order; lowerBound is P's ef-th key once P is full, else P's largest
+ * key, else FLT_MAX; N keeps its cap_n smallest entries, and an entry that falls off its end only matters (found =
+ * -1: the host re-runs the query on the bitmap walk) if it could still have been expanded (P not full, or its key
+ * <= lowerBound).  out_peak_n = the largest number of N entries that could still be expanded.                       */
 typedef struct { float k; uint32_t v; uint8_t x; } tl_ent;
 static int tl_listed(const tl_ent *a, int n, uint32_t id) { for (int i = 0; i < n; i++) if (a[i].v == id) return 1; return 0; }
 static void tl_insert(tl_ent *a, int *n, float key, uint32_t id, int expanded) {
@@ -685,14 +686,14 @@ ORC_API int orc_two_list_walk(const uint8_t *level0, uint64_t size_per_elem, uin
           if (tl_listed(P, sp, cid[j]) || tl_listed(N, sn, cid[j])) continue;
           TL_INSERT(ck[j], cid[j], cp[j], 0);
         }
-        if (sn > peak) peak = sn;
         if (sp >= ef) {
           sp = ef;
-          lb = P[ef - 1].k;
-          int w = 0;
-          for (int i = 0; i < sn; i++) if (!(N[i].k > lb)) N[w++] = N[i];
-          sn = w;
+          lb = P[ef - 1].k;   /* N is NOT pruned: entries beyond lowerBound are never expanded (break rule below) and are
+                                 the first to fall off N's end when it is full -- harmless, see `lost` */
         } else if (sp > 0) lb = pmax;
+        { int need = 0;       /* the capacity this query needs: N entries that may still be expanded */
+          for (int i = 0; i < sn; i++) need += (sp < ef) || !(N[i].k > lb);
+          if (need > peak) peak = need; }
         if (have_lost && !(sp >= ef && lost > lb)) { aborted = 1; break; }
       }
       if (nextkey > lb && (!size_guard || sp >= ef)) break;              /* :371 / :270 */

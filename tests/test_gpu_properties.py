@@ -168,10 +168,18 @@ def test_streamed_submit_wait_matches_blocking_calls(big):
     l, d = e.search(queries=Q[512:1024], k=10, ef=64)
     e.search_wait(t0)
     assert np.array_equal(l, ref[1][0]) and np.array_equal(outs[0][0], ref[0][0])
-    # too few results surface at wait()
-    with pytest.raises(RuntimeError, match='plain search only'):
-        e.set_option('force_general', 1)
-        try:
+    # the forced filtered / deletion-aware route is served by the streamed form too (hnsw_walk4f): the same rows
+    e.set_option('force_general', 1)
+    try:
+        t1 = e.search_submit(Q[:512], outs[1][0], outs[1][1], k=10, ef=64)
+        e.search_wait(t1)
+    finally:
+        e.set_option('force_general', 0)
+    assert np.array_equal(outs[1][0], ref[0][0]) and np.array_equal(bits(outs[1][1]), bits(ref[0][1]))
+    # ... but not by the bitmap walk
+    e.set_option('force_general', 2)
+    try:
+        with pytest.raises(RuntimeError, match='bitmap walk'):
             e.search_submit(Q[:8], outs[0][0][:8], outs[0][1][:8], k=10, ef=64)
-        finally:
-            e.set_option('force_general', 0)
+    finally:
+        e.set_option('force_general', 0)

@@ -244,7 +244,7 @@ def test_two_list_model_vs_oracle_on_fixtures(golden, mode):
 def walk4f_en_for(ef, s):
     """launch_walk4f's capacity rule for the traversed-only list (walk_flagged4.cu: walk4f_en_for)."""
     s = min(1.0, max(1e-4, s))
-    need = ef * (1 - s) / s + 5.0 * np.sqrt(ef * (1 - s)) / s + 16.0
+    need = ef * (1 - s) / s + 4.5 * np.sqrt(ef * (1 - s)) / s + 4.0
     return next((en for en in (2, 4, 8) if en * 32 >= need), 0)
 
 
