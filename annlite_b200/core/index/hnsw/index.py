@@ -135,14 +135,20 @@ class HnswIndex:
                 dists.sqrt_()
         return dists, ids
 
-    def search_batch_submit(self, queries, limit: int = 10):
-        """Streamed batched search for serving loops (no filter): returns a ticket at once, two batches can
-        be in flight so the transfers of one overlap the graph walk of the other."""
+    def search_batch_submit(self, queries, limit: int = 10, indices=None):
+        """Streamed batched search for serving loops: returns a ticket at once, two batches can be in flight so
+        the transfers (and the filter upload) of one overlap the graph walk of the other.  `indices` = the allowed
+        ids, as in `search` (hnsw/index.py:140-167)."""
         self._ensure_backend()
         if isinstance(queries, np.ndarray) or not hasattr(queries, 'data_ptr'):
             queries = self._prep(queries)
+        if indices is not None and len(indices) < limit:
+            raise ValueError('fewer allowed ids than `limit`: use search_batch (it shrinks the limit like the reference)')
+        from ...._lib import MAX_EF
+        if max(self.ef_search, limit) > MAX_EF:
+            raise ValueError(f'limit / ef_search above {MAX_EF} is not supported by the GPU walk (ANNB_MAX_EF)')
         self._index.set_ef(max(self.ef_search, limit))
-        return self._index.knn_query_submit(queries, k=limit, normalize=self._normalize_rounds)
+        return self._index.knn_query_submit(queries, k=limit, normalize=self._normalize_rounds, filters=indices)
 
     def search_batch_wait(self, ticket):
         ids, dists = self._index.knn_query_wait(ticket)

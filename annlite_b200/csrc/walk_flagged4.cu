@@ -405,11 +405,17 @@ int launch_walk4f_t(annb_index *h, const SearchParams &p_in) {
 template <int M>
 int launch_walk4f_m(annb_index *h, const SearchParams &p, int ep, int en) {
   if (ep == 2) {
-    if (en == 2) return launch_walk4f_t<M, 2, 2>(h, p);
-    if (en == 4) return launch_walk4f_t<M, 2, 4>(h, p);
-    return launch_walk4f_t<M, 2, 8>(h, p);
+    switch (en) {
+      case 2: return launch_walk4f_t<M, 2, 2>(h, p);
+      case 3: return launch_walk4f_t<M, 2, 3>(h, p);
+      case 4: return launch_walk4f_t<M, 2, 4>(h, p);
+      case 5: return launch_walk4f_t<M, 2, 5>(h, p);
+      case 6: return launch_walk4f_t<M, 2, 6>(h, p);
+      default: return launch_walk4f_t<M, 2, 8>(h, p);
+    }
   }
   if (en <= 4) return launch_walk4f_t<M, 4, 4>(h, p);
+  if (en <= 6) return launch_walk4f_t<M, 4, 6>(h, p);
   return launch_walk4f_t<M, 4, 8>(h, p);
 }
 
@@ -417,13 +423,15 @@ int launch_walk4f_m(annb_index *h, const SearchParams &p, int ep, int en) {
 
 // N's capacity for a filter (or deletion rate) that admits a fraction s of the nodes.  While P holds fewer than ef
 // entries N must keep every rejected node that was evaluated: a negative-binomial count with mean ef(1-s)/s and
-// variance ef(1-s)/s^2; afterwards it must keep the rejected nodes below lowerBound, the same count again.  Mean +
-// 4.5 sigma (one query in ~3e5 needs more; it is flagged and re-run on the bitmap walk).
+// variance ef(1-s)/s^2; afterwards it must keep the rejected nodes below lowerBound -- the same count again, but it is
+// the MAXIMUM of that count over the ~150 hops of a walk that has to fit.  Measured with the scalar model
+// (oracle.two_list_walk, ef = 64, s = 0.5: mean 64, sigma 11.3): the per-walk maximum has mean 77-84 and reached 123
+// in 3 000 walks, so mean + 4.5 sigma (128 entries) flags a query in every few thousand; mean + 6.5 sigma does not.
 static int walk4f_en_for(int ef, double s) {
   s = std::min(1.0, std::max(1e-4, s));
   const double mean = ef * (1.0 - s) / s, sd = std::sqrt(ef * (1.0 - s)) / s;
-  const double need = mean + 4.5 * sd + 4.0;
-  for (int en : {2, 4, 8})
+  const double need = mean + 6.5 * sd + 4.0;
+  for (int en : {2, 3, 4, 5, 6, 8})
     if (en * 32 >= need) return en;
   return 0;
 }
@@ -435,9 +443,9 @@ static bool walk4f_geometry(const annb_index *h, int ef, double selectivity, int
   if (ef > 128) return false;  // P wider than 4 entries per lane: the shared-memory merge of hnsw_walk_flagged
   const int ep = ef <= 64 ? 2 : 4;
   int en = walk4f_en_for(ef, selectivity);
-  if (h->opt_flagged_en == 2 || h->opt_flagged_en == 4 || h->opt_flagged_en == 8) en = (int)h->opt_flagged_en;  // tests: force an overflow
+  if (h->opt_flagged_en >= 2 && h->opt_flagged_en <= 8 && h->opt_flagged_en != 7) en = (int)h->opt_flagged_en;  // tests / A-B: force N's size
   if (en == 0) return false;
-  if (ep == 4 && en < 4) en = 4;
+  if (ep == 4) en = en <= 4 ? 4 : (en <= 6 ? 6 : 8);
   *ep_out = ep;
   *en_out = en;
   return true;

@@ -66,9 +66,7 @@ constexpr int w4_min_ctas(int M, int EPL) {  // register cap = 64K / (max thread
 }
 
 // =====================================================================================================
-// DIET (round 2, after the ncu reading of hnsw_walk4f): the nearest unexpanded entry as a per-lane (key, value) minimum
-// that is flagged by id, and the re-encounter check on KEYS first (ids only when a key matches).  Same walk.
-template <int M, int EPL, bool DIET>
+template <int M, int EPL>
 __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) hnsw_walk4(const GraphDev g, const SearchParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -179,25 +177,18 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
       // ---- nearest not-yet-expanded list entry == candidate_set.top() (:268).  It is the next node unless this
       // hop finds something closer, so its record is pulled into L2 FIRST: the DRAM round trip then overlaps the
       // whole hop, and a wrong guess still leaves the record in L2 for the hop that does expand it ----
-      uint32_t lm = KEY_MAX, lv = 0u;
-      if (DIET) {
-        unexpanded_min<EPL>(K, V, lm, lv);
-      } else {
+      uint32_t lm = KEY_MAX;
 #pragma unroll
-        for (int e = 0; e < EPL; e++) lm = min(lm, K[e] | (uint32_t)((int32_t)V[e] >> 31));
-      }
+      for (int e = 0; e < EPL; e++) lm = min(lm, K[e] | (uint32_t)((int32_t)V[e] >> 31));
       const uint32_t e2key = __reduce_min_sync(FULL_MASK, lm);
       int e2src = 0;
       uint32_t e2id = 0;
       if (e2key != KEY_MAX) {
         e2src = __ffs(__ballot_sync(FULL_MASK, lm == e2key)) - 1;
-        uint32_t myid = lv;  // DIET: an unexpanded entry's value is its node id
-        if (!DIET) {
-          myid = 0;
+        uint32_t myid = 0;
 #pragma unroll
-          for (int e = EPL - 1; e >= 0; e--)
-            if ((K[e] | (uint32_t)((int32_t)V[e] >> 31)) == e2key) myid = V[e] & IDM;  // lowest matching slot wins
-        }
+        for (int e = EPL - 1; e >= 0; e--)
+          if ((K[e] | (uint32_t)((int32_t)V[e] >> 31)) == e2key) myid = V[e] & IDM;  // lowest matching slot wins
         e2id = __shfl_sync(FULL_MASK, myid, e2src);
         // (an L2 prefetch, not a register load: a second load into the same registers would have to wait for
         // this one to land whenever a new candidate wins)
@@ -207,13 +198,9 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
           prefetch_l2(g.rec0 + (size_t)e2id * rec0_bytes + lane * 128u);
         }
       }
-      // expand that entry: flag it (the lowest matching slot of lane e2src; DIET: the slot that holds its id)
+      // expand that entry: flag it (the lowest matching slot of lane e2src)
       auto take_e2 = [&]() {
-        if (DIET) {
-#pragma unroll
-          for (int e = 0; e < EPL; e++)
-            if (V[e] == e2id) V[e] |= EXP_BIT;
-        } else if (lane == e2src) {
+        if (lane == e2src) {
           bool done = false;
 #pragma unroll
           for (int e = 0; e < EPL; e++) {
@@ -240,13 +227,7 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
       }
 
       // re-encounter of a listed node?  (an id can only be listed under this very key)
-      auto listed = [&](uint32_t key, uint32_t id) -> bool {
-        if (DIET) {
-          bool eq = false;
-#pragma unroll
-          for (int e = 0; e < EPL; e++) eq |= K[e] == key;
-          if (!__any_sync(FULL_MASK, eq)) return false;
-        }
+      auto listed = [&](uint32_t id) -> bool {
         bool dup = false;
 #pragma unroll
         for (int e = 0; e < EPL; e++) dup |= (V[e] & IDM) == id;
@@ -263,7 +244,7 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
         const int src = __ffs(__ballot_sync(FULL_MASK, mykey == mn)) - 1;  // lower lane first among equals
         id = __shfl_sync(FULL_MASK, cur.link, src);
         if (lane == src) mykey = KEY_MAX;
-        if (!listed(mn, id)) {
+        if (!listed(id)) {
           have_new = true;
           break;
         }
@@ -294,7 +275,7 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
           live &= live - 1;
           const uint32_t ck = __shfl_sync(FULL_MASK, mykey, src);
           const uint32_t cid = __shfl_sync(FULL_MASK, cur.link, src);
-          if (listed(ck, cid)) continue;
+          if (listed(cid)) continue;
           list_insert<EPL>(K, V, ck, cid, lane0);
           size++;
         }
@@ -362,12 +343,12 @@ __global__ void __launch_bounds__(w4_max_threads(M, EPL), w4_min_ctas(M, EPL)) h
   }
 }
 
-template <int M, int EPL, bool DIET>
-int launch_walk4_td(annb_index *h, const SearchParams &p_in) {
+template <int M, int EPL>
+int launch_walk4_t(annb_index *h, const SearchParams &p_in) {
   SearchParams p = p_in;
   p.prefetch = (int)h->opt_prefetch;
   static_assert(w4_fits(M, EPL, true) && w4_fits(M, EPL, false), "walk4 geometry exceeds the SM's shared memory");
-  auto kern = hnsw_walk4<M, EPL, DIET>;
+  auto kern = hnsw_walk4<M, EPL>;
   const bool fused = p.queries != nullptr;
   int warps = fused ? w4_cta_warps(M, EPL, true) : w4_cta_warps(M, EPL, false);
   int ctas = fused ? w4_ctas(M, EPL, true) : w4_ctas(M, EPL, false);
@@ -395,12 +376,6 @@ int launch_walk4_td(annb_index *h, const SearchParams &p_in) {
   h->launches++;
   ANNB_CUDA(cudaGetLastError());
   return ANNB_OK;
-}
-
-template <int M, int EPL>
-int launch_walk4_t(annb_index *h, const SearchParams &p) {
-  if (M == 8 && EPL == 2 && h->opt_walk_kernel == 3) return launch_walk4_td<M, EPL, M == 8 && EPL == 2>(h, p);  // A/B switch
-  return launch_walk4_td<M, EPL, false>(h, p);
 }
 
 template <int M>

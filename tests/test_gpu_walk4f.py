@@ -149,7 +149,7 @@ def test_streamed_filtered_search_equals_the_blocking_call():
     fl = torch.from_numpy(allow.view(np.int64)).pin_memory()
     outs = [(torch.empty((3000, 10), dtype=torch.int64).pin_memory(), torch.empty((3000, 10), dtype=torch.float32).pin_memory())
             for _ in range(4)]
-    n0 = e.launch_count
+    n0, fb0 = e.launch_count, e.fallback_count
     tk = []
     for i in range(4):
         if i >= 2:
@@ -158,7 +158,8 @@ def test_streamed_filtered_search_equals_the_blocking_call():
                                   filter_labels=fl.numpy().view(np.uint64)))
     e.search_wait(tk[2])
     e.search_wait(tk[3])
-    assert e.launch_count - n0 == 4 * 3                           # per batch: 2 bitmap kernels + ONE walk kernel
+    if e.fallback_count == fb0:                                    # (a flagged query would add its re-run's launches)
+        assert e.launch_count - n0 == 4 * 3                       # per batch: 2 bitmap kernels + ONE walk kernel
     for i in range(4):
         assert np.array_equal(outs[i][0].numpy().view(np.uint64), l) and np.array_equal(bits(outs[i][1].numpy()), bits(d))
     # device buffers, filter on the device

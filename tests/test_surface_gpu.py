@@ -144,9 +144,22 @@ def test_hnsw_index_matches_reference_semantics(golden, tmp_path):
     ds1, is1 = h.search_batch_wait(t1)
     ds2, is2 = h.search_batch_wait(t2)
     assert np.array_equal(np.vstack([is1, is2]), i1) and np.allclose(np.vstack([ds1, ds2]), d1, rtol=1e-6)
+    # ... with a filter too (annb_search_submit_filtered; every code geometry, not only hnsw_walk4f's)
+    df, jf = h.search_batch(golden.Q, limit=golden.k, indices=golden.allow)
+    t3 = h.search_batch_submit(golden.Q[:32], limit=golden.k, indices=golden.allow)
+    t4 = h.search_batch_submit(golden.Q[32:], limit=golden.k, indices=golden.allow)
+    ds3, is3 = h.search_batch_wait(t3)
+    ds4, is4 = h.search_batch_wait(t4)
+    assert np.array_equal(np.vstack([is3, is4]), jf) and np.allclose(np.vstack([ds3, ds4]), df, rtol=1e-6)
+    assert np.isin(jf, golden.allow).all()
     h.delete([int(golden.labels[0])])
     with pytest.raises(RuntimeError, match='update operation is not allowed'):
         h.update_with_ids(golden.X[:1], [0])
+    # after a deletion the streamed form still answers (deletion-aware walk), and never with the deleted id
+    t5 = h.search_batch_submit(golden.Q, limit=golden.k)
+    ds5, is5 = h.search_batch_wait(t5)
+    d5, i5 = h.search_batch(golden.Q, limit=golden.k)
+    assert np.array_equal(is5, i5) and not (is5 == golden.labels[0]).any()
 
 
 def test_pq_index_linear_scan(golden):

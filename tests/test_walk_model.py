@@ -244,8 +244,8 @@ def test_two_list_model_vs_oracle_on_fixtures(golden, mode):
 def walk4f_en_for(ef, s):
     """launch_walk4f's capacity rule for the traversed-only list (walk_flagged4.cu: walk4f_en_for)."""
     s = min(1.0, max(1e-4, s))
-    need = ef * (1 - s) / s + 4.5 * np.sqrt(ef * (1 - s)) / s + 4.0
-    return next((en for en in (2, 4, 8) if en * 32 >= need), 0)
+    need = ef * (1 - s) / s + 6.5 * np.sqrt(ef * (1 - s)) / s + 4.0
+    return next((en for en in (2, 3, 4, 5, 6, 8) if en * 32 >= need), 0)
 
 
 def test_two_list_model_capacity_rule_and_overflow_flag():
@@ -255,7 +255,7 @@ def test_two_list_model_capacity_rule_and_overflow_flag():
     g, t = _host_built(20000, 64, 8, 256, 21, threads=8)
     rng = np.random.default_rng(4)
     labels = g.labels()
-    for ef, s in ((64, 0.9), (64, 0.5), (64, 0.4), (128, 0.5), (10, 0.5), (100, 0.7)):
+    for ef, s in ((64, 0.9), (64, 0.5), (64, 0.45), (128, 0.6), (10, 0.5), (100, 0.7)):
         allow = labels[rng.random(g.n) < s]
         en = walk4f_en_for(ef, len(allow) / g.n)
         assert en > 0
