@@ -89,7 +89,10 @@ def c4(n=1_000_000, correlated=False):
     t_build = time.time() - t0
     l, d, st = e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow, with_stats=True)
     t_flt = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow), 3)
+    e.set_option('chunks', 1)                                      # one launch over the whole batch: the kernel's own time
+    e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow)
     k_ms = e.last_kernel_ms()['search_ms']
+    e.set_option('chunks', 0)
     t_plain = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2), 3)
     fb_batches, fb_queries = e.fallback_count, e.fallback_queries
     e.set_option('chunks', 1)                                      # one launch: the plain walk's kernel time on the same index
@@ -101,7 +104,7 @@ def c4(n=1_000_000, correlated=False):
     e.set_option('flagged_kernel', 1)
     l1, d1 = e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow)
     t_flt1 = timeit(lambda: e.search(queries=Q, k=a.k, ef=a.ef, normalize=2, filter_labels=allow), 3)
-    k_ms1 = e.last_kernel_ms()['search_ms']
+    k_ms1 = e.last_kernel_ms()['search_ms']                        # (round 1's kernel always runs as one launch)
     e.set_option('flagged_kernel', 0)
     same_as_round1 = tie_aware_rows(l, d, l1, d1).count('diff')
     # streamed form (annb_search_submit_filtered): pinned host buffers, two batches in flight, the filter label list
