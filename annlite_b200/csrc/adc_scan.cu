@@ -124,6 +124,109 @@ scan_topk_kernel(const float *__restrict__ tables, const code_t *__restrict__ co
   }
 }
 
+// ---- query-tiled scan (round 2): lanes = QUERIES, not rows --------------------------------------------------
+// scan_topk_kernel gives every warp its own table and lets its 32 lanes look up 32 DIFFERENT codes per step: 32
+// random words of a 256-entry row land in the 32 banks ~3.5 deep, and the measured rate is 15 % of the shared-memory
+// peak (bench.py k2_exhaustive_scan, 1M rows).  Here a CTA stages the tables of QT = 16 queries INTERLEAVED --
+// sT[(m*Ks + c)*16 + q] -- and a half-warp scores ONE row for those 16 queries: its 16 lanes read 16 consecutive
+// words (the code is the same for all of them), so a warp instruction touches two 64-byte runs: conflict-free or
+// 2-way.  The row's 8 code bytes are loaded once per 16 queries.  Every lane keeps the running top-KK of ITS
+// (query, row-parity) pair in registers (static indexing, bubble insertion -- rare once the threshold has settled);
+// the two halves are merged by shuffles, and the per-warp lists (G = chunks x warps per query) go to
+// merge_topk_kernel.  Same arithmetic (m sequential, fp32), same (dist, row) order: bit-identical results.
+constexpr int QT = 16;
+constexpr int TILED_WARPS = 16;
+
+template <int KK>
+__device__ __forceinline__ void lane_list_insert(float (&Kd)[KK], uint32_t (&Ki)[KK], float d, uint32_t id) {
+  if (d < Kd[KK - 1] || (d == Kd[KK - 1] && id < Ki[KK - 1])) {
+    Kd[KK - 1] = d;
+    Ki[KK - 1] = id;
+#pragma unroll
+    for (int i = KK - 1; i > 0; i--) {
+      const bool sw = Kd[i] < Kd[i - 1] || (Kd[i] == Kd[i - 1] && Ki[i] < Ki[i - 1]);
+      const float td = Kd[i];
+      const uint32_t ti = Ki[i];
+      Kd[i] = sw ? Kd[i - 1] : td;
+      Ki[i] = sw ? Ki[i - 1] : ti;
+      Kd[i - 1] = sw ? td : Kd[i - 1];
+      Ki[i - 1] = sw ? ti : Ki[i - 1];
+    }
+  }
+}
+
+template <int KK>
+__global__ void __launch_bounds__(TILED_WARPS * 32, 1)
+scan_topk_tiled_kernel(const float *__restrict__ tables, const uint8_t *__restrict__ codes, int64_t B, int64_t N, int Ks, int k,
+                       int chunks, int64_t rows_per_chunk, float *__restrict__ part_d, uint32_t *__restrict__ part_i) {
+  constexpr int M = 8;
+  extern __shared__ float sT[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, q = lane & 15;
+  const int64_t b0 = (int64_t)blockIdx.y * QT;
+  const int chunk = blockIdx.x;
+  const int TS = M * Ks;
+  // stage the tile: thread -> (table entry i, query q), q fastest => conflict-free shared-memory stores
+  for (int t = threadIdx.x; t < TS * QT; t += blockDim.x) {
+    const int qq = t & (QT - 1), i = t >> 4;
+    sT[t] = (b0 + qq < B) ? __ldg(tables + (b0 + qq) * TS + i) : 0.f;
+  }
+  __syncthreads();
+  float Kd[KK];
+  uint32_t Ki[KK];
+#pragma unroll
+  for (int i = 0; i < KK; i++) {
+    Kd[i] = CUDART_INF_F;
+    Ki[i] = LIST_EMPTY_VAL;
+  }
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = min(N, r0 + rows_per_chunk);
+  const float *Tq = sT + q;
+  auto score = [&](const uint2 c) -> float {  // m sequential from 0.f, every add rounded (pq_bindings.pyx:30-47)
+    float d = 0.f;
+    d = __fadd_rn(d, Tq[(0 * Ks + (int)(c.x & 0xff)) * QT]);
+    d = __fadd_rn(d, Tq[(1 * Ks + (int)((c.x >> 8) & 0xff)) * QT]);
+    d = __fadd_rn(d, Tq[(2 * Ks + (int)((c.x >> 16) & 0xff)) * QT]);
+    d = __fadd_rn(d, Tq[(3 * Ks + (int)(c.x >> 24)) * QT]);
+    d = __fadd_rn(d, Tq[(4 * Ks + (int)(c.y & 0xff)) * QT]);
+    d = __fadd_rn(d, Tq[(5 * Ks + (int)((c.y >> 8) & 0xff)) * QT]);
+    d = __fadd_rn(d, Tq[(6 * Ks + (int)((c.y >> 16) & 0xff)) * QT]);
+    d = __fadd_rn(d, Tq[(7 * Ks + (int)(c.y >> 24)) * QT]);
+    return d;
+  };
+  // two rows per lane and iteration: two independent lookup chains in flight (16 warps per SM is all the tile leaves room for)
+  constexpr int64_t STEP = 2 * TILED_WARPS;
+  int64_t r = r0 + 2 * warp + half;
+  for (; r + STEP < r1; r += 2 * STEP) {
+    const uint2 ca = __ldg(reinterpret_cast<const uint2 *>(codes + r * 8));
+    const uint2 cb = __ldg(reinterpret_cast<const uint2 *>(codes + (r + STEP) * 8));
+    const float da = score(ca), db = score(cb);
+    lane_list_insert<KK>(Kd, Ki, da, (uint32_t)r);
+    lane_list_insert<KK>(Kd, Ki, db, (uint32_t)(r + STEP));
+  }
+  if (r < r1) {
+    const uint2 ca = __ldg(reinterpret_cast<const uint2 *>(codes + r * 8));
+    lane_list_insert<KK>(Kd, Ki, score(ca), (uint32_t)r);
+  }
+  // the odd-row half hands its list to the even-row half of the same query
+#pragma unroll
+  for (int i = 0; i < KK; i++) {
+    const float od = __shfl_down_sync(FULL_MASK, Kd[i], 16);
+    const uint32_t oi = __shfl_down_sync(FULL_MASK, Ki[i], 16);
+    if (half == 0 && oi != LIST_EMPTY_VAL) lane_list_insert<KK>(Kd, Ki, od, oi);
+  }
+  if (half == 0 && b0 + q < B) {
+    const int64_t G = (int64_t)chunks * TILED_WARPS;
+    const int64_t o = ((b0 + q) * G + (int64_t)chunk * TILED_WARPS + warp) * k;
+#pragma unroll
+    for (int i = 0; i < KK; i++)
+      if (i < k) {
+        part_d[o + i] = Kd[i];
+        part_i[o + i] = Ki[i];
+      }
+  }
+}
+
 // Merge G sorted (ascending) lists of k (dist, id) per query into the global k best, ordered
 // by (dist, id).  One warp per query; lists are tiny (G*k entries).  Used for chunk partials
 // (ids = u32 row index -> i64) and for shard results (ids = u64 labels).
@@ -219,6 +322,45 @@ static int run_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k,
   return ANNB_OK;
 }
 
+// the query-tiled scan: M = 8 one-byte codes, a 16-query interleaved tile that fits shared memory, k <= 16 (per-lane
+// register lists), enough queries to fill tiles and enough rows to amortise staging a 128 KB tile
+template <int KK>
+static int run_scan_topk_tiled(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists) {
+  const int64_t N = h->n_codes;
+  const size_t smem = (size_t)h->M * h->Ks * QT * sizeof(float);
+  auto kern = scan_topk_tiled_kernel<KK>;
+  ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (B + QT - 1) / QT;
+  // one CTA per SM is resident (the tile): ~2 waves of CTAs, at most 16 chunks (the merge sees chunks x 16 lists)
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (2LL * h->sm_count + tiles - 1) / tiles));
+  chunks = (int)std::min<int64_t>(chunks, std::max<int64_t>(1, N / 4096));
+  int64_t rows_per_chunk = (N + chunks - 1) / chunks;
+  rows_per_chunk = (rows_per_chunk + 31) / 32 * 32;
+  chunks = (int)std::max<int64_t>(1, (N + rows_per_chunk - 1) / rows_per_chunk);
+  const int G = chunks * TILED_WARPS;
+  float *part_d;
+  uint32_t *part_i;
+  int rc;
+  if ((rc = annb_scratch(h, 16, (size_t)B * G * k * sizeof(float), (void **)&part_d))) return rc;
+  if ((rc = annb_scratch(h, 17, (size_t)B * G * k * sizeof(uint32_t), (void **)&part_i))) return rc;
+  int64_t done = 0;
+  while (done < B) {
+    const int64_t nb = std::min<int64_t>(B - done, (int64_t)65535 * QT);
+    dim3 grid((unsigned)chunks, (unsigned)((nb + QT - 1) / QT));
+    kern<<<grid, TILED_WARPS * 32, smem, h->stream>>>(d_tables + done * h->M * h->Ks, (const uint8_t *)h->d_codes, nb, N, h->Ks, k, chunks,
+                                                      rows_per_chunk, part_d + done * G * k, part_i + done * G * k);
+    h->launches++;
+    ANNB_CUDA(cudaGetLastError());
+    done += nb;
+  }
+  const int warps = 4;
+  merge_topk_kernel<uint32_t, int64_t, 1><<<(unsigned)((B + warps - 1) / warps), warps * 32, 0, h->stream>>>(
+      part_d, part_i, G, B, k, (int64_t)k, (int64_t)G * k, d_dists, d_ids, LIST_EMPTY_VAL, (int64_t)-1);
+  h->launches++;
+  ANNB_CUDA(cudaGetLastError());
+  return ANNB_OK;
+}
+
 int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists) {
   if (B == 0) return ANNB_OK;
   const int64_t N = h->n_codes;
@@ -226,6 +368,12 @@ int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int
   if (N >= (int64_t)0xffffffffll) ANNB_FAIL(ANNB_ELIMIT, "scan supports < 2^32-1 rows per index (shard larger sets)");
   const size_t tbytes = (size_t)h->M * h->Ks * sizeof(float);
   const size_t lim = smem_optin_limit(h->device);
+  if (h->opt_scan_kernel != 1 && h->M == 8 && h->code_bytes == 1 && k <= 16 && tbytes * QT + 1024 <= lim &&
+      ((B >= 64 && N >= 32768) || h->opt_scan_kernel == 2)) {
+    if (k <= 1) return run_scan_topk_tiled<1>(h, d_tables, B, k, d_ids, d_dists);
+    if (k <= 10) return run_scan_topk_tiled<10>(h, d_tables, B, k, d_ids, d_dists);
+    return run_scan_topk_tiled<16>(h, d_tables, B, k, d_ids, d_dists);
+  }
   int W = 8;
   int in_smem = 1;
   while (W > 1 && W * tbytes > lim - 1024) W >>= 1;

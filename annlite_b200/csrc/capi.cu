@@ -215,9 +215,6 @@ int annb_stream(annb_index_t *h, uint64_t *stream_out) {
 }
 
 static int lane_wait(annb_index *h, int lane);
-static int submit_impl(annb_index *h, const float *queries, int in_space, int64_t B, int normalize, int k, int ef,
-                       const uint64_t *filter_labels, int filter_space, int64_t n_filter, uint64_t *labels_out, float *dists_out,
-                       int out_space, int *ticket_out);
 int annb_sync(annb_index_t *h) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
@@ -991,29 +988,6 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
   if (h->gd.n == 0) {  // empty index: searchKnn returns nothing (hnswalg.h:1240)
     ANNB_FAIL(ANNB_EFEWRESULTS, "Cannot return the results in a contigious 2D array. Probably ef or M is too small");
   }
-  // ---- host buffers, filter and/or deletions: the two halves of the batch go through the two streamed lanes
-  // (submit_impl: upload, filter bitmap, hnsw_walk4f, download -- each half entirely on its own stream), so the
-  // copies and the bitmap build of one half and the under-occupied tail of its launch overlap the other half's walk
-  if (queries && in_space != ANNB_DEVICE && host_out && !stats_out && B >= 4096 && h->opt_chunks != 1 && h->opt_force_general != 2 &&
-      (filter_labels || h->g.num_deleted > 0 || h->opt_force_general) && walk4_can_fuse(h)) {
-    const double s_ = filter_labels ? std::min<double>(1.0, (double)n_filter / (double)std::max<int64_t>(1, h->gd.n))
-                                    : 1.0 - (double)h->g.num_deleted / (double)std::max<int64_t>(1, h->gd.n);
-    if (walk4f_applicable(h, ef_eff, s_)) {
-      int tk[2] = {-1, -1};
-      int rc = ANNB_OK;
-      for (int c = 0; c < 2 && rc == ANNB_OK; c++) {
-        const int64_t b0 = B * c / 2, nb = B * (c + 1) / 2 - b0;
-        rc = submit_impl(h, queries + b0 * h->dim, in_space, nb, normalize, k, ef, filter_labels, filter_space, n_filter,
-                         labels_out + b0 * k, dists_out + b0 * k, out_space, &tk[c]);
-      }
-      for (int c = 0; c < 2; c++)   // wait for what was enqueued even after a failure: the buffers are the caller's
-        if (tk[c] >= 0) {
-          const int rw = lane_wait(h, tk[c] & 1);
-          if (rc == ANNB_OK) rc = rw;
-        }
-      return rc;
-    }
-  }
   // ---- host-buffer fast path: chunked two-stream pipeline -------------------------------------------
   // H2D of chunk c+1 overlaps the walk of chunk c, the walk of chunk c+1 fills the SMs that chunk c's
   // persistent launch leaves idle in its tail, and D2H of chunk c overlaps the walk of chunk c+1.
@@ -1573,6 +1547,7 @@ int annb_set_option(annb_index_t *h, const char *name, int64_t value) {
   else if (!strcmp(name, "flagged_epl")) h->opt_flagged_epl = value;
   else if (!strcmp(name, "flagged_kernel")) h->opt_flagged_kernel = value;
   else if (!strcmp(name, "flagged_en")) h->opt_flagged_en = value;
+  else if (!strcmp(name, "scan_kernel")) h->opt_scan_kernel = value;
   else if (!strcmp(name, "walk_kernel")) h->opt_walk_kernel = value;
   else if (!strcmp(name, "dump_tables")) h->opt_dump_tables = value;
   else if (!strcmp(name, "prefetch")) h->opt_prefetch = value;

@@ -441,14 +441,21 @@ def run_ours(a):
             # lookup per (query, row, subquantiser); an SM serves 32 four-byte lookups per clock
             e.scan_topk(tables=tbl, k=k)
             k2_ms = e.last_kernel_ms()['scan_ms']
+            e.set_option('scan_kernel', 1)       # round 1's kernel (lanes = rows, one table per warp) for the before/after
+            gt_old, _ = e.scan_topk(tables=tbl, k=k)
+            e.scan_topk(tables=tbl, k=k)
+            k2_ms_old = e.last_kernel_ms()['scan_ms']
+            e.set_option('scan_kernel', 0)
             if k2_ms and k2_ms > 0:
                 peak_lk = 148 * 32 * (ck['sm_mhz'] or 1965.0) * 1e6 if isinstance(ck, dict) else 148 * 32 * 1.965e9
                 lk = float(sample) * n * a.m
-                k2 = {'kernel': 'scan_topk_kernel + merge_topk_kernel', 'queries': int(sample), 'rows': int(n),
+                k2 = {'kernel': 'scan_topk_tiled_kernel (16-query interleaved table tile, lanes = queries) + merge_topk_kernel',
+                      'round1_kernel_ms': round(k2_ms_old, 3), 'ids_equal_round1_kernel': bool(np.array_equal(gt_i, gt_old)),
+                      'queries': int(sample), 'rows': int(n),
                       'ms': round(k2_ms, 3), 'qps': round(sample / (k2_ms / 1e3), 1), 'bound': 'shared-memory gather',
                       'lookups_per_s': round(lk / (k2_ms / 1e3), 1), 'peak_lookups_per_s': peak_lk,
                       'frac': round(lk / (k2_ms / 1e3) / peak_lk, 4), 'hbm_bytes_algorithmic': int(n * a.m * ((sample + 7) // 8)),
-                      'note': 'untimed side measurement (not part of value / e2e): 8 query tables per CTA share one pass over the codes'}
+                      'note': 'untimed side measurement (not part of value / e2e)'}
         Xd = torch.from_numpy(make_base(a)).cuda()
         qd = Qd[0][:sample]
         d2 = (qd * qd).sum(1, keepdim=True) - 2 * qd @ Xd.T + (Xd * Xd).sum(1)[None]

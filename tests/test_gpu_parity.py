@@ -238,3 +238,38 @@ def test_encode_matches_exact_argmin(golden):
     assert mism <= 2e-3, mism       # fp32 vs fp64 evaluation differ on near-ties only
     vs_ref = float((c != golden.codes).mean())   # golden.codes = scipy vq inside the reference
     assert vs_ref <= 5e-3, vs_ref
+
+
+# ---- K2, query-tiled kernel (scan_topk_tiled_kernel: lanes = queries, interleaved 16-query table tile) ---------
+@pytest.mark.parametrize('k', [1, 7, 10, 16])
+@pytest.mark.parametrize('N,B,Ks,ties', [(100_000, 200, 256, False), (40_000, 70, 256, True), (33_000, 64, 200, False),
+                                         (2_500, 37, 256, False)])
+def test_k2_tiled_scan_topk_ids_exact(N, B, Ks, ties, k):
+    """ids and distance bits equal to the oracle's (dist, row) order, and to the round-1 kernel's; `ties` = a
+    codebook of small integers, so many rows have exactly equal distances; the last shape forces the tiled
+    kernel on an input the dispatcher would leave to the round-1 kernel (ragged tile, rows not a multiple of 32)."""
+    rng = np.random.default_rng(N + B + k)
+    cb = rng.standard_normal((8, Ks, 4)).astype(np.float32)
+    if ties:
+        cb = np.round(cb)
+    codes = rng.integers(0, Ks, (N, 8)).astype(np.uint8)
+    q = rng.standard_normal((B, 32)).astype(np.float32)
+    if ties:
+        q = np.round(q)
+    e = Engine(32, 8, Ks)
+    e.set_codebook(cb)
+    e.set_codes(codes)
+    t = O.adc_table(q, cb)
+    e.set_option('scan_kernel', 2)
+    n0 = e.launch_count
+    ids, d = e.scan_topk(tables=t, k=k)
+    assert e.launch_count - n0 == 2            # the tiled scan + the merge of the per-warp partial lists
+    e.set_option('scan_kernel', 1)
+    ids1, d1 = e.scan_topk(tables=t, k=k)
+    e.set_option('scan_kernel', 0)
+    rid, rd = O.scan_topk(t, codes, k)
+    assert np.array_equal(ids, rid) and np.array_equal(bits(d), bits(rd))
+    assert np.array_equal(ids1, rid) and np.array_equal(bits(d1), bits(rd))
+    if N >= 32768 and B >= 64:                 # ... and it is what the dispatcher picks at this size
+        ids0, d0 = e.scan_topk(queries=q, k=k)
+        assert np.array_equal(ids0, rid) and np.array_equal(bits(d0), bits(rd))

@@ -195,27 +195,3 @@ def test_streamed_filtered_search_equals_the_blocking_call():
     assert not np.isin(ld, dead).any()
     assert np.array_equal(outs[1][0].numpy().view(np.uint64), ld) and np.array_equal(bits(outs[1][1].numpy()), bits(dd))
 
-
-def test_blocking_filtered_call_with_host_buffers_runs_on_both_lanes():
-    """>= 4096 host queries with a filter (or deletions): annb_search sends the two halves through the two streamed
-    lanes; the rows are those of the single-launch call."""
-    N = 20000
-    e, cb, Q, labels, rng = make(N, 128, 8, 995, nq=5000)
-    allow = labels[rng.random(N) < 0.5]
-    e.set_option('chunks', 1)
-    l1, d1 = e.search(queries=Q, k=10, ef=64, filter_labels=allow)
-    e.set_option('chunks', 0)
-    n0 = e.launch_count
-    l2, d2 = e.search(queries=Q, k=10, ef=64, filter_labels=allow)
-    assert e.launch_count - n0 >= 6                                   # two halves: 2 x (bitmap build + walk)
-    assert np.array_equal(l1, l2) and np.array_equal(bits(d1), bits(d2))
-    with pytest.raises(RuntimeError, match='Cannot return the results in a contigious 2D array'):
-        e.search(queries=Q, k=10, ef=64, filter_labels=labels[:3])
-    dead = labels[rng.random(N) < 0.3]
-    for x in dead:
-        e.mark_deleted(int(x))
-    e.set_option('chunks', 1)
-    l3, d3 = e.search(queries=Q, k=10, ef=64)
-    e.set_option('chunks', 0)
-    l4, d4 = e.search(queries=Q, k=10, ef=64)
-    assert np.array_equal(l3, l4) and np.array_equal(bits(d3), bits(d4)) and not np.isin(l4, dead).any()
