@@ -227,6 +227,135 @@ scan_topk_tiled_kernel(const float *__restrict__ tables, const uint8_t *__restri
   }
 }
 
+// ---- the same, on a diet (ncu of the first version: 73 warp instructions per two-row step, 4.5 ms for 1000 queries x
+// 1M rows, and 3 ms more in the merge of the 16 x chunks per-warp lists): Ks = 256 at compile time (lookup = byte
+// extract + shift + LDS with an immediate row offset), the threshold test of the streaming loop compares distances only
+// (rows arrive in ascending order, so an equal distance never displaces), and the CTA reduces its 16 per-warp lists
+// to ONE list per (query, chunk) through shared memory before anything is written.
+template <int KK>
+__device__ __forceinline__ void lane_list_insert_ascending_rows(float (&Kd)[KK], uint32_t (&Ki)[KK], float d, uint32_t id) {
+  if (d < Kd[KK - 1]) {
+    Kd[KK - 1] = d;
+    Ki[KK - 1] = id;
+#pragma unroll
+    for (int i = KK - 1; i > 0; i--) {
+      const bool sw = Kd[i] < Kd[i - 1];
+      const float td = Kd[i];
+      const uint32_t ti = Ki[i];
+      Kd[i] = sw ? Kd[i - 1] : td;
+      Ki[i] = sw ? Ki[i - 1] : ti;
+      Kd[i - 1] = sw ? td : Kd[i - 1];
+      Ki[i - 1] = sw ? ti : Ki[i - 1];
+    }
+  }
+}
+
+template <int KK>
+__global__ void __launch_bounds__(TILED_WARPS * 32, 1)
+scan_topk_tiled2_kernel(const float *__restrict__ tables, const uint8_t *__restrict__ codes, int64_t B, int64_t N, int k, int chunks,
+                        int64_t rows_per_chunk, float *__restrict__ part_d, uint32_t *__restrict__ part_i) {
+  constexpr int M = 8, KS = 256;
+  extern __shared__ float sT[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, q = lane & 15;
+  const int64_t b0 = (int64_t)blockIdx.y * QT;
+  const int chunk = blockIdx.x;
+  constexpr int TS = M * KS;
+  for (int t = threadIdx.x; t < TS * QT; t += blockDim.x) {
+    const int qq = t & (QT - 1), i = t >> 4;
+    sT[t] = (b0 + qq < B) ? __ldg(tables + (b0 + qq) * TS + i) : 0.f;
+  }
+  __syncthreads();
+  float Kd[KK];
+  uint32_t Ki[KK];
+#pragma unroll
+  for (int i = 0; i < KK; i++) {
+    Kd[i] = CUDART_INF_F;
+    Ki[i] = LIST_EMPTY_VAL;
+  }
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = min(N, r0 + rows_per_chunk);
+  const float *Tq = sT + q;
+  auto score = [&](const uint2 c) -> float {  // m sequential from 0.f, every add rounded (pq_bindings.pyx:30-47)
+    float d = 0.f;
+    d = __fadd_rn(d, Tq[((c.x & 0xffu) + 0 * KS) * QT]);
+    d = __fadd_rn(d, Tq[(((c.x >> 8) & 0xffu) + 1 * KS) * QT]);
+    d = __fadd_rn(d, Tq[(((c.x >> 16) & 0xffu) + 2 * KS) * QT]);
+    d = __fadd_rn(d, Tq[((c.x >> 24) + 3 * KS) * QT]);
+    d = __fadd_rn(d, Tq[((c.y & 0xffu) + 4 * KS) * QT]);
+    d = __fadd_rn(d, Tq[(((c.y >> 8) & 0xffu) + 5 * KS) * QT]);
+    d = __fadd_rn(d, Tq[(((c.y >> 16) & 0xffu) + 6 * KS) * QT]);
+    d = __fadd_rn(d, Tq[((c.y >> 24) + 7 * KS) * QT]);
+    return d;
+  };
+  constexpr int64_t STEP = 2 * TILED_WARPS;
+  int64_t r = r0 + 2 * warp + half;
+  for (; r + STEP < r1; r += 2 * STEP) {
+    const uint2 ca = __ldg(reinterpret_cast<const uint2 *>(codes + r * 8));
+    const uint2 cb = __ldg(reinterpret_cast<const uint2 *>(codes + (r + STEP) * 8));
+    const float da = score(ca), db = score(cb);
+    lane_list_insert_ascending_rows<KK>(Kd, Ki, da, (uint32_t)r);
+    lane_list_insert_ascending_rows<KK>(Kd, Ki, db, (uint32_t)(r + STEP));
+  }
+  if (r < r1) {
+    const uint2 ca = __ldg(reinterpret_cast<const uint2 *>(codes + r * 8));
+    lane_list_insert_ascending_rows<KK>(Kd, Ki, score(ca), (uint32_t)r);
+  }
+  // the odd-row half hands its list to the even-row half of the same query: (dist, row) order from here on
+#pragma unroll
+  for (int i = 0; i < KK; i++) {
+    const float od = __shfl_down_sync(FULL_MASK, Kd[i], 16);
+    const uint32_t oi = __shfl_down_sync(FULL_MASK, Ki[i], 16);
+    if (half == 0 && oi != LIST_EMPTY_VAL) lane_list_insert<KK>(Kd, Ki, od, oi);
+  }
+  // ---- CTA reduction: the 16 per-warp lists of a query -> one list, through the (no longer needed) table area ----
+  __syncthreads();  // every warp is done with the tables
+  float *sd = sT;
+  uint32_t *si = reinterpret_cast<uint32_t *>(sT + QT * TILED_WARPS * KK);
+  if (half == 0) {
+#pragma unroll
+    for (int i = 0; i < KK; i++) {
+      sd[(q * TILED_WARPS + warp) * KK + i] = Kd[i];
+      si[(q * TILED_WARPS + warp) * KK + i] = Ki[i];
+    }
+  }
+  __syncthreads();
+  // warp w finishes query w: lane l < 16 holds the list warp l produced, the other lanes hold empty lists
+#pragma unroll
+  for (int i = 0; i < KK; i++) {
+    Kd[i] = half == 0 ? sd[(warp * TILED_WARPS + q) * KK + i] : CUDART_INF_F;
+    Ki[i] = half == 0 ? si[(warp * TILED_WARPS + q) * KK + i] : LIST_EMPTY_VAL;
+  }
+  const int64_t b = b0 + warp;
+  const int64_t o = (b * chunks + chunk) * k;
+  for (int j = 0; j < k; j++) {
+    float md = Kd[0];
+    uint32_t mi = Ki[0];
+#pragma unroll
+    for (int s2 = 16; s2 > 0; s2 >>= 1) {
+      const float od = __shfl_xor_sync(FULL_MASK, md, s2);
+      const uint32_t oi = __shfl_xor_sync(FULL_MASK, mi, s2);
+      if (od < md || (od == md && oi < mi)) {
+        md = od;
+        mi = oi;
+      }
+    }
+    if (lane == 0 && b < B) {
+      part_d[o + j] = md;
+      part_i[o + j] = mi;
+    }
+    if (Ki[0] == mi && mi != LIST_EMPTY_VAL) {  // row ids are unique across the lists: exactly one lane pops its head
+#pragma unroll
+      for (int i = 0; i + 1 < KK; i++) {
+        Kd[i] = Kd[i + 1];
+        Ki[i] = Ki[i + 1];
+      }
+      Kd[KK - 1] = CUDART_INF_F;
+      Ki[KK - 1] = LIST_EMPTY_VAL;
+    }
+  }
+}
+
 // Merge G sorted (ascending) lists of k (dist, id) per query into the global k best, ordered
 // by (dist, id).  One warp per query; lists are tiny (G*k entries).  Used for chunk partials
 // (ids = u32 row index -> i64) and for shard results (ids = u64 labels).
@@ -328,8 +457,11 @@ template <int KK>
 static int run_scan_topk_tiled(annb_index *h, const float *d_tables, int64_t B, int k, int64_t *d_ids, float *d_dists) {
   const int64_t N = h->n_codes;
   const size_t smem = (size_t)h->M * h->Ks * QT * sizeof(float);
+  const bool v2 = h->Ks == 256 && h->opt_scan_kernel != 3;   // the diet version: Ks = 256, one list per (query, chunk)
   auto kern = scan_topk_tiled_kernel<KK>;
-  ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern2 = scan_topk_tiled2_kernel<KK>;
+  if (v2) ANNB_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else ANNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (B + QT - 1) / QT;
   // one CTA per SM is resident (the tile): ~2 waves of CTAs, at most 16 chunks (the merge sees chunks x 16 lists)
   int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (2LL * h->sm_count + tiles - 1) / tiles));
@@ -337,7 +469,7 @@ static int run_scan_topk_tiled(annb_index *h, const float *d_tables, int64_t B, 
   int64_t rows_per_chunk = (N + chunks - 1) / chunks;
   rows_per_chunk = (rows_per_chunk + 31) / 32 * 32;
   chunks = (int)std::max<int64_t>(1, (N + rows_per_chunk - 1) / rows_per_chunk);
-  const int G = chunks * TILED_WARPS;
+  const int G = v2 ? chunks : chunks * TILED_WARPS;
   float *part_d;
   uint32_t *part_i;
   int rc;
@@ -347,8 +479,12 @@ static int run_scan_topk_tiled(annb_index *h, const float *d_tables, int64_t B, 
   while (done < B) {
     const int64_t nb = std::min<int64_t>(B - done, (int64_t)65535 * QT);
     dim3 grid((unsigned)chunks, (unsigned)((nb + QT - 1) / QT));
-    kern<<<grid, TILED_WARPS * 32, smem, h->stream>>>(d_tables + done * h->M * h->Ks, (const uint8_t *)h->d_codes, nb, N, h->Ks, k, chunks,
-                                                      rows_per_chunk, part_d + done * G * k, part_i + done * G * k);
+    if (v2)
+      kern2<<<grid, TILED_WARPS * 32, smem, h->stream>>>(d_tables + done * h->M * h->Ks, (const uint8_t *)h->d_codes, nb, N, k, chunks,
+                                                         rows_per_chunk, part_d + done * G * k, part_i + done * G * k);
+    else
+      kern<<<grid, TILED_WARPS * 32, smem, h->stream>>>(d_tables + done * h->M * h->Ks, (const uint8_t *)h->d_codes, nb, N, h->Ks, k, chunks,
+                                                        rows_per_chunk, part_d + done * G * k, part_i + done * G * k);
     h->launches++;
     ANNB_CUDA(cudaGetLastError());
     done += nb;
@@ -369,7 +505,7 @@ int launch_scan_topk(annb_index *h, const float *d_tables, int64_t B, int k, int
   const size_t tbytes = (size_t)h->M * h->Ks * sizeof(float);
   const size_t lim = smem_optin_limit(h->device);
   if (h->opt_scan_kernel != 1 && h->M == 8 && h->code_bytes == 1 && k <= 16 && tbytes * QT + 1024 <= lim &&
-      ((B >= 64 && N >= 32768) || h->opt_scan_kernel == 2)) {
+      ((B >= 64 && N >= 32768) || h->opt_scan_kernel >= 2)) {
     if (k <= 1) return run_scan_topk_tiled<1>(h, d_tables, B, k, d_ids, d_dists);
     if (k <= 10) return run_scan_topk_tiled<10>(h, d_tables, B, k, d_ids, d_dists);
     return run_scan_topk_tiled<16>(h, d_tables, B, k, d_ids, d_dists);
