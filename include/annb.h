@@ -262,6 +262,13 @@ ANNB_API int annb_fallback_queries(annb_index_t *h, int64_t *out);
  * a small host insertion rewrote were uploaded (the reference searches the structure it inserts into: hnswalg.h:1108;
  * here insertions happen on the host graph and the walk layout on the device follows). */
 ANNB_API int annb_sync_counts(annb_index_t *h, int64_t *full_syncs, int64_t *patches);
+/* Tuning / A-B / test switches (none changes results): "chunks" (host-buffer pipeline depth of annb_search, 1 = off),
+ * "walk_kernel" (plain search: 0 hnsw_walk4 fused, 2 hnsw_walk4 over K1 tables, 1 round-1 kernels), "flagged_kernel"
+ * (filter / deletions: 0 hnsw_walk4f where it applies, 1 hnsw_walk_flagged), "flagged_en" (force hnsw_walk4f's
+ * traversed-only list to 32 x value entries), "flagged_epl" (force hnsw_walk_flagged with 32 x value entries),
+ * "force_general" (1 = filtered route without a filter, 2 = bitmap walk), "scan_kernel" (K2: 0 query-tiled where it
+ * applies, 1 round-1 kernel, 2 tiled even for small inputs, 3 first tiled version), "prefetch", "warps_per_cta",
+ * "ctas_per_sm", "gpu_build", "gpu_build_frac", "timing", "ip_raw", "dump_tables", "reset_counters". */
 ANNB_API int annb_set_option(annb_index_t *h, const char *name, int64_t value);
 
 #ifdef __cplusplus
