@@ -35,6 +35,29 @@ sys.path.insert(0, ROOT)
 CACHE = os.path.join(ROOT, '.index_cache')
 
 
+def filtered_leg(timeout_s=240):
+    """configs[3] (1M cosine, random 50 % filter, ef=64, k=10, 10 000-query batches) as an UNTIMED side measurement
+    after the headline legs: `scripts/bench_configs.py c4` in a child process, so that nothing there can take the
+    headline line with it.  Reports the filtered walk's kernel time, the streamed (annb_search_submit_filtered, pinned
+    buffers, two batches in flight) and blocking end-to-end rates, and parity against the oracle's filtered search on
+    a 2 000-query sample of the same graph."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'bench_configs.py'), 'c4'], cwd=ROOT,
+                           env=dict(os.environ, C4_SKIP_REF='1'), capture_output=True, text=True, timeout=timeout_s)
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1])
+        keep = ('config', 'filtered_kernel', 'gpu_filtered_kernel_ms', 'gpu_filtered_qps_streamed_host_buffers',
+                'streamed_ms_per_batch', 'streamed_rows_equal_blocking_call', 'gpu_filtered_qps_host_buffers',
+                'flagged_walk_fallback_queries', 'round1_flagged_walk', 'unfiltered_kernel_ms', 'hops_per_query',
+                'unfiltered_hops_per_query', 'all_results_pass_filter', 'parity_sample', 'rows_exact', 'rows_tie', 'rows_diff',
+                'recall_vs_oracle_ids', 'max_rel_dist_err_equal_ids')
+        out = {k_: d.get(k_) for k_ in keep}
+        out['note'] = ('untimed side measurement in a child process; cosine => the device l2_normalize makes distance BITS '
+                       'differ on part of the rows (rows_diff) at <= 1e-6 relative, ids are the oracle\'s (recall_vs_oracle_ids)')
+        return out
+    except Exception as ex:   # never at the expense of the headline line
+        return {'unavailable': repr(ex)[:300]}
+
+
 def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -59,6 +82,8 @@ def parse(argv=None):
     ap.add_argument('--ref-sample', type=int, default=10000)
     ap.add_argument('--chunks', type=int, default=0, help='host-buffer pipeline depth inside annb_search (0 = auto)')
     ap.add_argument('--pool', type=int, default=4, help='distinct query batches cycled through the steps')
+    ap.add_argument('--no-filtered-leg', action='store_true',
+                    help='skip the configs[3] side measurement (filtered search, child process, ~20 s, untimed)')
     return ap.parse_args(argv)
 
 
@@ -449,7 +474,7 @@ def run_ours(a):
             if k2_ms and k2_ms > 0:
                 peak_lk = 148 * 32 * (ck['sm_mhz'] or 1965.0) * 1e6 if isinstance(ck, dict) else 148 * 32 * 1.965e9
                 lk = float(sample) * n * a.m
-                k2 = {'kernel': 'scan_topk_tiled_kernel (16-query interleaved table tile, lanes = queries) + merge_topk_kernel',
+                k2 = {'kernel': 'scan_topk_tiled2_kernel (16-query interleaved table tile, lanes = queries) + merge_topk_kernel',
                       'round1_kernel_ms': round(k2_ms_old, 3), 'ids_equal_round1_kernel': bool(np.array_equal(gt_i, gt_old)),
                       'queries': int(sample), 'rows': int(n),
                       'ms': round(k2_ms, 3), 'qps': round(sample / (k2_ms / 1e3), 1), 'bound': 'shared-memory gather',
@@ -498,6 +523,8 @@ def run_ours(a):
                     result[key] = shard_res[key]
                 result['e2e'] = dict(result['e2e'], **shard_res['e2e'], api='ShardedEngine: submit + all-gather + merge, 2 batches in flight')
                 result['config']['parallelism'] = f'shard{world}'
+        if world == 1 and a.steps >= 20 and not a.no_filtered_leg and a.n == 1_000_000 and a.metric == 'euclidean':
+            result['filtered_configs3'] = filtered_leg()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
