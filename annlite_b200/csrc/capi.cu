@@ -215,6 +215,25 @@ int annb_stream(annb_index_t *h, uint64_t *stream_out) {
 }
 
 static int lane_wait(annb_index *h, int lane);
+static int lane_rerun_flagged(annb_index *h, int lane, int64_t n_over);
+
+// A streamed filtered batch whose walk flagged queries is finished (those queries re-run on the bitmap walk) out of
+// the lane's own scratch: queries, filter bitmap, device outputs.  Lane 0 shares these buffers with the blocking entry
+// points, so they settle such a batch before they touch them; its ticket stays open for annb_search_wait, which then
+// only reports `< k` results.
+static int settle_flagged_lanes(annb_index *h) {
+  for (int lane = 0; lane < 2; lane++) {
+    annb_index::AsyncLane &L = h->lanes[lane];
+    if (!L.busy || !L.flagged) continue;
+    ANNB_CUDA(cudaStreamSynchronize(lane ? h->stream2 : h->stream));
+    int64_t n_over = 0;
+    for (int64_t b = 0; b < L.B; b++) n_over += L.hfound[b] < 0;
+    if (n_over) ANNB_TRY(lane_rerun_flagged(h, lane, n_over));
+    L.flagged = false;
+  }
+  return ANNB_OK;
+}
+
 int annb_sync(annb_index_t *h) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
@@ -268,6 +287,7 @@ static void fuse_params(annb_index *h, SearchParams &p, const float *d_queries) 
 int annb_adc_table(annb_index_t *h, const float *queries, int q_space, int64_t B, int normalize, float *out, int out_space) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if (B < 0 || (B > 0 && (!queries || !out))) ANNB_FAIL(ANNB_EINVAL, "null queries/out");
   if (B == 0) return ANNB_OK;
   const size_t tbytes = (size_t)B * h->M * h->Ks * sizeof(float);
@@ -324,6 +344,7 @@ int annb_set_codes(annb_index_t *h, const void *codes, int space, int64_t n) {
 int annb_scan(annb_index_t *h, const float *table, int t_space, float *out_dists, int out_space) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if (!table || !out_dists) ANNB_FAIL(ANNB_EINVAL, "null table/out");
   if (!h->d_codes) ANNB_FAIL(ANNB_ESTATE, "no code matrix: call annb_set_codes first");
   const float *dt;
@@ -344,6 +365,7 @@ int annb_scan_topk(annb_index_t *h, const float *queries, const float *tables, i
                    float *dists, int out_space) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if ((queries == nullptr) == (tables == nullptr)) ANNB_FAIL(ANNB_EINVAL, "exactly one of queries / tables must be given");
   if (B < 0 || k <= 0 || !ids || !dists) ANNB_FAIL(ANNB_EINVAL, "bad B/k/outputs");
   if (!h->d_codes) ANNB_FAIL(ANNB_ESTATE, "no code matrix: call annb_set_codes first");
@@ -523,6 +545,7 @@ int annb_get_graph(annb_index_t *h, uint8_t *data_level0, uint8_t *link_lists, i
 int annb_encode(annb_index_t *h, const float *vectors, int v_space, int64_t n, void *codes, int c_space) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if (n < 0 || (n > 0 && (!vectors || !codes))) ANNB_FAIL(ANNB_EINVAL, "null vectors/codes");
   if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
   if (n == 0) return ANNB_OK;
@@ -584,6 +607,7 @@ static const float *feed_next(void *ctx, int64_t first, int64_t cnt) {
 int annb_add_items(annb_index_t *h, const float *vectors, const void *codes, const uint64_t *labels, int64_t n, int num_threads) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if (n < 0 || (n > 0 && (!vectors || !labels))) ANNB_FAIL(ANNB_EINVAL, "null vectors/labels");
   if (!h->d_codebook) ANNB_FAIL(ANNB_ESTATE, "Please train the PQ before using HNSW quantization backend");
   if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised: call annb_init_graph first");
@@ -964,6 +988,7 @@ int annb_search(annb_index_t *h, const float *queries, const float *tables, int 
                 float *dists_out, int out_space, int64_t *stats_out) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if ((queries == nullptr) == (tables == nullptr)) ANNB_FAIL(ANNB_EINVAL, "exactly one of queries / tables must be given");
   if (B < 0 || k <= 0 || ef <= 0 || !labels_out || !dists_out) ANNB_FAIL(ANNB_EINVAL, "bad B/k/ef/outputs");
   if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");
@@ -1175,6 +1200,7 @@ int annb_scan_subset(annb_index_t *h, const float *queries, int in_space, int64_
                      const uint64_t *subset_labels, int64_t n_subset, uint64_t *labels_out, float *dists_out) {
   ANNB_ENTER(h);
   ANNB_NEED_GPU(h);
+  ANNB_TRY(settle_flagged_lanes(h));
   if (!queries || !labels_out || !dists_out || B < 0 || k <= 0 || n_subset < 0 || (n_subset > 0 && !subset_labels))
     ANNB_FAIL(ANNB_EINVAL, "bad arguments");
   if (!h->g.inited) ANNB_FAIL(ANNB_ESTATE, "index not initialised");

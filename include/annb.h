@@ -222,7 +222,9 @@ ANNB_API int annb_scan_subset(annb_index_t *h, const float *queries, int in_spac
  * annb_search_submit_filtered = knn_query_with_filter (bindings/hnsw_bindings.cpp:393-516) in the same form: the
  * filter label list is uploaded and turned into the by-id bitmap on the batch's own lane; filter_labels == NULL means
  * no filter, a non-NULL list with n_filter == 0 admits nothing.  Queries whose walk outgrew the register lists are
- * re-run on the bitmap walk inside annb_search_wait (annb_fallback_queries counts them). */
+ * re-run on the bitmap walk inside annb_search_wait (annb_fallback_queries counts them) -- or earlier, by the next
+ * blocking call on the handle (annb_search, annb_scan_topk, annb_adc_table, annb_add_items, ...): those share device
+ * scratch with lane 0 and first settle any such batch, whose ticket stays valid for annb_search_wait. */
 ANNB_API int annb_search_submit(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize, int k,
                        int ef, uint64_t *labels_out, float *dists_out, int out_space, int *ticket_out);
 ANNB_API int annb_search_submit_filtered(annb_index_t *h, const float *queries, int in_space, int64_t B, int normalize,
