@@ -34,8 +34,9 @@
 // pruned per hop.
 //
 // Differences from the reference are confined to exact fp32 ties (arrival order instead of heap order), as for
-// every single-list walk here; tests/test_gpu_walk4.py checks ids, distance bits, hop and neighbour counts against
-// the oracle on every tie-free walk.
+// every single-list walk here; tests/test_gpu_walk4f.py checks ids, distance bits, hop and neighbour counts against
+// the oracle on every tie-free walk, tests/test_walk_model.py the scalar model of this walk (oracle.two_list_walk)
+// against the restatement of the reference on the CPU.
 #include <math_constants.h>
 
 #include <algorithm>
